@@ -1,0 +1,275 @@
+"""Parity of the sm_100a path (through the C ABI) with the CPU oracle and the golden vectors made from the reference.
+
+Tolerances (BASELINE.json north_star): log-mel max-abs-err <= 1e-3 vs the reference extractor; padding, attention
+masks and labels bit-exact."""
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_DIR, ROOT, check_against_golden, golden_logmel_cases
+from oracle import collate as ocollate
+from oracle import logmel as ologmel
+from oracle import signals
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3  # north_star tolerance on (log10(mel)+4)/4 features
+
+import asr_finetune_b200 as pkg  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def fe128():
+    assert torch.cuda.is_available(), "the -m gpu suite needs a CUDA device"
+    return pkg.WhisperFeatureExtractor(feature_size=128)
+
+
+@pytest.fixture(scope="module")
+def fe80():
+    return pkg.WhisperFeatureExtractor(feature_size=80)
+
+
+CASES = golden_logmel_cases()
+
+
+@pytest.mark.parametrize("key,n_mel,gen", CASES, ids=[c[0] for c in CASES])
+def test_reference_call_matches_golden(logmel_golden, fe128, fe80, key, n_mel, gen):
+    fe = fe128 if n_mel == 128 else fe80
+    before = pkg._lib.launch_count()
+    # exactly the reference's call (ref:finetune/training/data_and_collator/datasets_and_collators.py:194-195)
+    out = fe(gen(), sampling_rate=16000).input_features[0]
+    assert pkg._lib.launch_count() > before, "no CUDA kernel ran"
+    assert isinstance(out, np.ndarray) and out.shape == (n_mel, 3000) and out.dtype == np.float32
+    check_against_golden(out, logmel_golden, key, "t", TOL)  # torch fp32 path = what the reference runs
+    check_against_golden(out, logmel_golden, key, "n", TOL)  # numpy fp64 path
+
+
+def test_known_answers(fe128):
+    z = fe128(np.zeros(480000, np.float32), sampling_rate=16000).input_features[0]
+    assert (z == -1.5).all()  # all-zero audio -> exactly -1.5
+    one = fe128(np.ones(480000, np.float32), sampling_rate=16000).input_features[0]
+    assert abs(one.max() - 1.6206918) < 1e-4 and abs(one.min() + 0.37930822) < 1e-4
+    tone = fe128(signals.named_case("tone1k"), sampling_rate=16000).input_features[0]
+    assert abs(tone.max() - 1.474446) < 1e-4 and abs((tone.max() - tone.min()) - 2.0) < 1e-5
+    assert int(tone.argmax()) // 3000 == 42
+
+
+def test_config1_16_clips_full_resolution_vs_oracle(fe128):
+    # BASELINE configs[0]: large-v3 (128 mel), 16 synthetic 30-s clips, CPU numpy reference
+    clips = [signals.noise(i, 480000) for i in range(12)] + [signals.named_case(n) for n in
+                                                            ("chirp", "am", "speechlike", "noise_q16")]
+    out = fe128(clips, sampling_rate=16000, return_tensors="pt")["input_features"]
+    assert out.dtype == torch.float32 and tuple(out.shape) == (16, 128, 3000) and not out.is_cuda
+    worst = 0.0
+    for i, c in enumerate(clips):
+        ref = ologmel.logmel_clip(c, 128, "fp64")
+        worst = max(worst, float(np.abs(out[i].numpy() - ref).max()))
+    assert worst <= TOL, worst
+    print(f"config1 max-abs-err vs fp64 oracle: {worst:.3e}")
+
+
+def test_batch_is_per_clip_max_and_mask_is_bit_exact(logmel_golden, fe128):
+    trio = [signals.named_case("tone1k"), signals.named_case("tone1k_quiet"), signals.noise(7, 112123)]
+    bf = fe128(trio, sampling_rate=16000, return_tensors="pt", return_attention_mask=True)
+    assert bf["attention_mask"].dtype == torch.int32
+    np.testing.assert_array_equal(bf["attention_mask"].numpy(), logmel_golden["batch3/attention_mask"])
+    feats = bf["input_features"].numpy()
+    for i in range(3):
+        assert np.abs(feats[i][:, ::25] - logmel_golden[f"batch3/{i}/sub"]).max() <= TOL
+        assert abs(float(feats[i].max()) - logmel_golden[f"batch3/{i}/stats"][0]) <= TOL
+    # batch composition must not change a clip's result (clamp is per clip): bit-exact vs the single call
+    alone = fe128(trio[1], sampling_rate=16000).input_features[0]
+    np.testing.assert_array_equal(alone, feats[1])
+
+
+def test_full_resolution_short_clip_and_normalize(logmel_golden, fe128):
+    out = fe128(signals.noise(100 + 16000 % 97, 16000), sampling_rate=16000).input_features[0]
+    assert np.abs(out - logmel_golden["full/noise_len16000_128"]).max() <= TOL
+    outn = fe128(signals.noise(7, 112123), sampling_rate=16000, do_normalize=True).input_features[0]
+    assert np.abs(outn[:, ::25] - logmel_golden["normalize/noise_len112123_128"]).max() <= TOL
+
+
+def test_dtype_and_container_variants(fe80):
+    clip = signals.noise(11, 50000)
+    a = fe80(clip, sampling_rate=16000).input_features[0]
+    b = fe80(clip.astype(np.float64), sampling_rate=16000).input_features[0]  # fp64 -> fp32 cast (HF ...:285-286)
+    c = fe80(clip.tolist()[:4000] + [0.0] * 0, sampling_rate=16000).input_features[0]
+    np.testing.assert_array_equal(a, b)
+    ref_c = ologmel.logmel_clip(clip[:4000], 80, "fp64")
+    assert np.abs(c - ref_c).max() <= TOL
+    d = fe80(clip[None, :], sampling_rate=16000).input_features  # 2-D numpy = batch of 1
+    np.testing.assert_array_equal(d[0], a)
+    long = signals.noise(12, 640000)  # 40 s -> truncated to 30 s, mask sum 3000
+    e = fe80(long, sampling_rate=16000, return_attention_mask=True)
+    f = fe80(long[:480000], sampling_rate=16000).input_features[0]
+    np.testing.assert_array_equal(e.input_features[0], f)
+    assert int(e["attention_mask"].sum()) == 3000
+
+
+def test_int16_pcm_ingest_matches_dequantised_float(fe128):
+    x = signals.noise(21, 200000)
+    q = np.clip(np.round(x.astype(np.float64) * 32768.0), -32768, 32767).astype(np.int16)
+    dev = fe128.cuda_device()
+    pcm = torch.from_numpy(q).to(dev)
+    offs = torch.tensor([0, len(q)], dtype=torch.int64, device=dev)
+    feats, _ = fe128.logmel_device(pcm, offs, 1, pcm_scale=1.0 / 32768.0)
+    ref = ologmel.logmel_clip((q.astype(np.float32) / np.float32(32768.0)), 128, "fp64")
+    assert np.abs(feats[0].cpu().numpy() - ref).max() <= TOL
+
+
+def _config3(batch, seed=1337):
+    lens = signals.clip_lengths(seed, batch)
+    clips = [signals.noise(1000 + i, int(n)) if i % 3 else signals.speechlike(i, int(n)) for i, n in enumerate(lens)]
+    return lens, clips, signals.label_ids(seed, batch, 5, 448)
+
+
+def test_config3_variable_length_masks_labels_bit_exact(fe128):
+    # BASELINE configs[2] at a batch the oracle finishes in seconds: ragged clips 1-30 s, masks, labels, BOS strip
+    B = 24
+    lens, clips, labels = _config3(B)
+    dev = fe128.cuda_device()
+    pcm = torch.from_numpy(np.concatenate(clips)).to(dev)
+    offs = torch.from_numpy(np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)).to(dev)
+    feats, mask = fe128.logmel_device(pcm, offs, B, return_attention_mask=True)
+    assert torch.equal(mask.cpu(), torch.from_numpy(ologmel.frame_attention_mask(lens)))
+    worst = max(float(np.abs(feats[i].cpu().numpy() - ologmel.logmel_clip(clips[i], 128, "fp64")).max()) for i in range(B))
+    assert worst <= TOL, worst
+    coll = pkg.DataCollatorSpeechSeq2SeqWithPadding(processor=type("P", (), {"feature_extractor": fe128})(),
+                                                    decoder_start_token_id=signals.SOT)
+    batch = coll({"input_features": [f for f in feats], "labels": labels})  # device-resident features: one gather kernel
+    f_ref, l_ref = ocollate.collate_padding([f.cpu().numpy() for f in feats], labels, signals.EOT, signals.SOT)
+    assert batch["labels"].dtype == torch.int64 and batch["labels"].is_cuda
+    assert torch.equal(batch["labels"].cpu(), torch.from_numpy(l_ref))
+    assert tuple(batch["labels"].shape) == (B, max(len(x) for x in labels) - 1)  # BOS column stripped
+    assert torch.equal(batch["input_features"].cpu(), torch.from_numpy(f_ref))
+
+
+def _collate_meta():
+    with open(os.path.join(GOLDEN_DIR, "collate_golden.json")) as f:
+        return json.load(f)["cases"]
+
+
+@pytest.mark.parametrize("case", _collate_meta(), ids=[c["key"] for c in _collate_meta()])
+def test_collator_matches_reference_golden(collate_golden, case):
+    import hashlib
+
+    sys.path.insert(0, GOLDEN_DIR)
+    from make_golden import fake_features
+
+    key = case["key"]
+    flat, offs = collate_golden[f"{key}/ids_flat"], collate_golden[f"{key}/ids_offsets"]
+    labels_in = [flat[offs[i]:offs[i + 1]].tolist() for i in range(len(offs) - 1)]
+    feats = fake_features(case["seed"], case["batch"], case["n_mel"])
+    fe = pkg.WhisperFeatureExtractor(feature_size=case["n_mel"])
+    coll = pkg.DataCollatorSpeechSeq2SeqWithPadding(processor=type("P", (), {"feature_extractor": fe, "tokenizer": None})(),
+                                                    decoder_start_token_id=signals.SOT)
+    # host numpy features, as the reference's eval loop feeds them (ref:finetune/evaluation/evaluate_model.py:279-282)
+    out = coll({"input_features": feats, "labels": labels_in})
+    assert torch.equal(out["labels"].cpu(), torch.from_numpy(collate_golden[f"{key}/labels"]))
+    assert hashlib.sha256(out["input_features"].cpu().numpy().tobytes()).hexdigest() == case["features_sha256"]
+    # device-resident features take the fused gather path of the same kernel
+    out_d = coll({"input_features": [torch.from_numpy(f).cuda() for f in feats], "labels": labels_in})
+    assert torch.equal(out_d["input_features"], out["input_features"]) and torch.equal(out_d["labels"], out["labels"])
+    # streaming collator: same padding, NO BOS strip (reference quirk)
+    _, lab_s = pkg.collator.collate_labels_and_features(fe, labels_in, None, width=None, decoder_start_token_id=-1,
+                                                        strip_bos=False)
+    assert torch.equal(lab_s.cpu(), torch.from_numpy(collate_golden[f"{key}/labels_streaming"]))
+
+
+def test_fixed_448_labels(collate_golden, fe80):
+    out = pkg.labels_fixed_length(fe80, collate_golden["fixed448/ids"].tolist(), 448)
+    assert torch.equal(out.cpu(), torch.from_numpy(collate_golden["fixed448/labels"]))
+
+
+def test_streaming_collator_end_to_end(fe128):
+    B = 6
+    lens, clips, labels = _config3(B, seed=7)
+    coll = pkg.StreamingFrontendCollator(fe128)
+    out = coll({"audio": clips, "labels": labels})
+    assert out["input_features"].is_cuda and tuple(out["input_features"].shape) == (B, 128, 3000)
+    ref = ologmel.logmel_batch(clips, 128, "fp64")
+    assert np.abs(out["input_features"].cpu().numpy() - ref).max() <= TOL
+    _, l_ref = ocollate.collate_streaming([r for r in ref], labels, signals.EOT)
+    assert torch.equal(out["labels"].cpu(), torch.from_numpy(l_ref))
+    with pytest.raises(RuntimeError, match="No valid data in batch"):
+        coll({"audio": [], "labels": []})
+
+
+def test_raw_c_abi_with_plain_pointers(fe80):
+    # straight through include/wfe.h: device pointers + sizes, explicit stream, no torch types in the call
+    lib = pkg._lib.load()
+    h = fe80._handle(None, fe80.cuda_device())
+    clip = signals.chirp(n=300000)
+    dev = fe80.cuda_device()
+    pcm = torch.from_numpy(clip).to(dev)
+    offs = torch.tensor([0, 300000], dtype=torch.int64, device=dev)
+    out = torch.empty((1, 80, 3000), dtype=torch.float32, device=dev)
+    mask = torch.empty((1, 3000), dtype=torch.int32, device=dev)
+    scratch = torch.empty(lib.wfe_logmel_scratch_bytes(h.ptr, 1), dtype=torch.uint8, device=dev)
+    st = torch.cuda.Stream(dev)
+    st.wait_stream(torch.cuda.current_stream(dev))
+    n0 = lib.wfe_launch_count()
+    rc = lib.wfe_logmel(h.ptr, pcm.data_ptr(), 0, 1.0, offs.data_ptr(), 1, None, out.data_ptr(), mask.data_ptr(),
+                        scratch.data_ptr(), C.c_void_p(st.cuda_stream))
+    assert rc == 0, lib.wfe_last_error()
+    st.synchronize()
+    assert lib.wfe_launch_count() == n0 + 1
+    assert np.abs(out[0].cpu().numpy() - ologmel.logmel_clip(clip, 80, "fp64")).max() <= TOL
+    assert int(mask.sum()) == 1875
+    # errors come back as status + message, never as exceptions across the ABI
+    assert lib.wfe_logmel(h.ptr, None, 0, 1.0, offs.data_ptr(), 1, None, out.data_ptr(), None, scratch.data_ptr(), None) == -1
+    assert b"null" in lib.wfe_last_error()
+    assert lib.wfe_logmel(h.ptr, pcm.data_ptr(), 7, 1.0, offs.data_ptr(), 1, None, out.data_ptr(), None, scratch.data_ptr(), None) == -1
+    assert lib.wfe_logmel(h.ptr, pcm.data_ptr(), 0, 1.0, offs.data_ptr(), 0, None, out.data_ptr(), None, scratch.data_ptr(), None) == 0
+
+
+def test_properties_at_full_size_config2(fe80):
+    # BASELINE configs[1]: whisper-small 80-mel, batch 256 x 30 s on one B200 — size-independent properties
+    B = 256
+    dev = fe80.cuda_device()
+    base = torch.from_numpy(np.stack([signals.noise(i, 480000) for i in range(8)])).to(dev)
+    gains = torch.tensor([10.0 ** (-(i // 8) / 16.0) for i in range(B)], device=dev).view(B // 8, 8, 1)
+    pcm = (base.unsqueeze(0) * gains).reshape(B, 480000).contiguous()  # clip b = base[b % 8] * gain[b // 8]
+    offs = torch.arange(B + 1, dtype=torch.int64, device=dev) * 480000
+    feats, _ = fe80.logmel_device(pcm.view(-1), offs, B)
+    feats2, _ = fe80.logmel_device(pcm.view(-1), offs, B)
+    assert torch.equal(feats, feats2)  # deterministic / idempotent
+    assert torch.isfinite(feats).all()
+    # range property of the clamp: max - min <= 2.0 per clip ((g-8+4)/4 floor)
+    span = feats.amax(dim=(1, 2)) - feats.amin(dim=(1, 2))
+    assert float(span.max()) <= 2.0 + 1e-6
+    # gain property: scaling a clip by a shifts every unclamped feature by log10(a^2)/4 = log10(a)/2
+    f = feats.view(B // 8, 8, 80, 3000)
+    for j in (1, 7, 31):
+        shift = float(torch.log10(gains[j, 0, 0])) / 2.0
+        assert float((f[j] - f[0] - shift).abs().max()) <= 2e-4
+    # spot check against the oracle at both ends of the batch
+    for b in (0, 255):
+        ref = ologmel.logmel_clip(pcm[b].cpu().numpy(), 80, "fp64")
+        assert np.abs(feats[b].cpu().numpy() - ref).max() <= TOL
+
+
+def test_zero_padded_tail_is_the_clamp_floor_and_edges(fe128):
+    clip = signals.noise(5, 16000)
+    out = fe128(clip, sampling_rate=16000).input_features[0]
+    # frames whose window lies entirely in the zero padding: max(-10, gmax-8) -> ((.)+4)/4, a single constant
+    tail = out[:, 102:]
+    assert (tail == tail[0, 0]).all()
+    g = (out.max() * 4.0 - 4.0)
+    assert abs(tail[0, 0] - (max(-10.0, g - 8.0) + 4.0) / 4.0) <= 1e-5
+    for n in (1, 3, 159, 160, 161, 399, 400, 401):
+        c = signals.noise(n, n)
+        o = fe128(c, sampling_rate=16000).input_features[0]
+        assert np.abs(o - ologmel.logmel_clip(c, 128, "fp64")).max() <= TOL, n
+
+
+def test_host_entry_reports_pcie_bytes(fe128):
+    clips = [signals.noise(i, 100000 + 1000 * i) for i in range(5)]
+    fe128(clips, sampling_rate=16000)
+    up, down = fe128.last_transfer_bytes
+    assert up == sum(len(c) for c in clips) * 4 + 6 * 8  # ragged: only real samples cross PCIe (+ offsets)
+    assert down == 5 * 128 * 3000 * 4
