@@ -53,9 +53,9 @@ def load() -> C.CDLL:
     lib.wfe_logmel_scratch_bytes.restype = C.c_size_t
     lib.wfe_n_frames.argtypes = [vp]
     lib.wfe_n_frames.restype = i32
-    lib.wfe_logmel.argtypes = [vp, vp, i32, f32, vp, i32, vp, vp, vp, vp, vp]
+    lib.wfe_logmel.argtypes = [vp, vp, i32, f32, vp, vp, i32, vp, vp, vp, vp, vp]
     lib.wfe_logmel.restype = C.c_int
-    lib.wfe_clip_stats.argtypes = [vp, vp, i32, f32, vp, i32, vp, vp]
+    lib.wfe_clip_stats.argtypes = [vp, vp, i32, f32, vp, vp, i32, vp, vp]
     lib.wfe_clip_stats.restype = C.c_int
     lib.wfe_collate.argtypes = [vp, vp, vp, i32, i32, i64, i64, vp, vp, vp, i64, vp, vp]
     lib.wfe_collate.restype = C.c_int

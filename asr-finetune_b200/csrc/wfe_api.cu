@@ -55,13 +55,14 @@ struct HostSlot {
   void* h_in = nullptr;      // pinned, chunk * n_samples * 4 B
   float* h_out = nullptr;    // pinned, chunk * n_mel * n_frames floats
   int32_t* h_mask = nullptr;
-  int64_t* h_off = nullptr;  // pinned, chunk + 1
+  int64_t* h_off = nullptr;  // pinned, 2 * chunk: clip starts (16-byte aligned), then clip lengths
   void* d_in = nullptr;
   float* d_out = nullptr;
   int32_t* d_mask = nullptr;
   int64_t* d_off = nullptr;
   void* d_scratch = nullptr;
   float* d_stats = nullptr;
+  int64_t* d_len = nullptr;
   // pending finalisation (pageable destination)
   float* user_out = nullptr;
   int32_t* user_mask = nullptr;
@@ -72,9 +73,11 @@ struct HostSlot {
 
 struct wfe_handle {
   wfe_config cfg;
-  int n_frames = 0, ntiles = 0, nnz = 0;
-  int2* d_mel_tab = nullptr;
-  int32_t* d_mel_start = nullptr;
+  int n_frames = 0, ntiles = 0, n_units = 0, n_ksteps = 0, sm_count = 0;
+  int ctas_per_sm[2] = {0, 0};   // resident CTAs of logmel_kernel<float>, <int16_t>
+  float4* d_s1_consts = nullptr;       // [8][25]
+  float2* d_mel_btab = nullptr;        // [n_ksteps][32]
+  wfe::MelUnit* d_mel_units = nullptr; // [n_units]
   std::mutex host_mu;
   bool ring_ready = false;
   int chunk_clips = 16;
@@ -83,48 +86,64 @@ struct wfe_handle {
 
 namespace {
 
-using wfe::bin_to_row;
-
-int upload_constants() {
-  float win[wfe::kNFft];
-  float2 tw[16 * 12];
-  wfe::fill_tables(win, tw);
-  WFE_CUDA(cudaMemcpyToSymbol(wfe::c_win, win, sizeof(win)));
-  WFE_CUDA(cudaMemcpyToSymbol(wfe::c_tw400, tw, sizeof(tw)));
-  return WFE_OK;
+// round-to-nearest (ties away) fp32 -> tf32, like cvt.rna.tf32.f32
+float tf32_rna(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  u = (u + 0x1000u) & 0xffffe000u;
+  float r;
+  memcpy(&r, &u, 4);
+  return r;
 }
 
-size_t scratch_bytes(const wfe_handle* h, int batch) {
-  return (size_t)batch * (2 * sizeof(uint32_t) + (size_t)h->ntiles * sizeof(float));
+size_t scratch_bytes(const wfe_handle*, int batch) {
+  // clip_key[B], clip_ticket[B], tile_counter (+ pad to 16 B)
+  return ((size_t)batch * 2 + 4) * sizeof(uint32_t);
 }
 
 template <typename T>
-int launch_logmel(wfe_handle* h, const void* pcm, float scale, const int64_t* offsets, int batch, const float* norm,
-                  float* out, int32_t* mask, void* scratch, cudaStream_t st) {
+int launch_logmel(wfe_handle* h, const void* pcm, float scale, const int64_t* offsets, const int64_t* lengths, int batch,
+                  const float* norm, float* out, int32_t* mask, void* scratch, cudaStream_t st) {
   static_assert(sizeof(T) == 2 || sizeof(T) == 4, "pcm dtype");
+  const long long total = (long long)batch * h->ntiles;
+  if (total > 0x7fffffffLL) return fail(WFE_ERR_INVALID, "batch too large for one launch");
   wfe::LogmelParams p;
   p.pcm = pcm;
   p.offsets = offsets;
+  p.lengths = lengths;
   p.norm = reinterpret_cast<const float2*>(norm);
   p.out = out;
   p.mask = mask;
   p.clip_key = reinterpret_cast<uint32_t*>(scratch);
   p.clip_ticket = p.clip_key + batch;
-  p.tile_min = reinterpret_cast<float*>(p.clip_ticket + batch);
-  p.mel_tab = h->d_mel_tab;
-  p.mel_start = h->d_mel_start;
+  p.tile_counter = p.clip_ticket + batch;
+  p.s1_consts = h->d_s1_consts;
+  p.mel_btab = h->d_mel_btab;
+  p.mel_units = h->d_mel_units;
   p.pcm_scale = scale;
   p.n_mel = h->cfg.n_mel;
   p.n_samples = h->cfg.n_samples;
   p.n_frames = h->n_frames;
   p.ntiles = h->ntiles;
-  WFE_CUDA(cudaMemsetAsync(scratch, 0, (size_t)batch * 2 * sizeof(uint32_t), st));
-  // opt in to > 48 KB dynamic shared memory (cheap; per device context, so done on every launch)
-  WFE_CUDA(cudaFuncSetAttribute(wfe::logmel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)wfe::kSmemBytes));
-  const long long grid = (long long)batch * h->ntiles;
-  if (grid > 2147483647LL) return fail(WFE_ERR_INVALID, "batch too large for one launch");
-  wfe::logmel_kernel<T><<<(unsigned)grid, wfe::kThreads, wfe::kSmemBytes, st>>>(p);
+  p.n_units = h->n_units;
+  p.n_ksteps = h->n_ksteps;
+  p.total_tiles = (uint32_t)total;
+  WFE_CUDA(cudaMemsetAsync(scratch, 0, scratch_bytes(h, batch), st));
+  const size_t smem = wfe::logmel_smem_bytes(h->n_ksteps);
+  const int which = sizeof(T) == 4 ? 0 : 1;
+  if (h->ctas_per_sm[which] == 0) {
+    // opt in to > 48 KB dynamic shared memory (per function, shared by every handle: always the maximum any filter
+    // bank can need) and size the persistent grid from the real occupancy
+    WFE_CUDA(cudaFuncSetAttribute(wfe::logmel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)wfe::logmel_smem_bytes(wfe::kMaxKsteps)));
+    int n = 0;
+    WFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, wfe::logmel_kernel<T>, wfe::kThreads, smem));
+    if (n < 1) return fail(WFE_ERR_CUDA, "logmel kernel does not fit on an SM");
+    h->ctas_per_sm[which] = n;
+  }
+  long long grid = (long long)h->sm_count * h->ctas_per_sm[which];
+  if (grid > total) grid = total;
+  wfe::logmel_kernel<T><<<(unsigned)grid, wfe::kThreads, smem, st>>>(p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   WFE_CUDA(cudaGetLastError());
   return WFE_OK;
@@ -157,6 +176,7 @@ void free_ring(wfe_handle* h) {
     if (s.d_off) cudaFree(s.d_off);
     if (s.d_scratch) cudaFree(s.d_scratch);
     if (s.d_stats) cudaFree(s.d_stats);
+    if (s.d_len) cudaFree(s.d_len);
     if (s.done) cudaEventDestroy(s.done);
     if (s.stream) cudaStreamDestroy(s.stream);
     s = HostSlot();
@@ -167,7 +187,7 @@ void free_ring(wfe_handle* h) {
 int ensure_ring(wfe_handle* h) {
   if (h->ring_ready) return WFE_OK;
   const size_t c = (size_t)h->chunk_clips;
-  const size_t in_bytes = c * h->cfg.n_samples * sizeof(float);
+  const size_t in_bytes = c * ((size_t)h->cfg.n_samples + 8) * sizeof(float);
   const size_t out_elems = c * h->cfg.n_mel * h->n_frames;
   for (auto& s : h->slots) {
     WFE_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
@@ -175,11 +195,11 @@ int ensure_ring(wfe_handle* h) {
     WFE_CUDA(cudaHostAlloc(&s.h_in, in_bytes, cudaHostAllocDefault));
     WFE_CUDA(cudaHostAlloc((void**)&s.h_out, out_elems * sizeof(float), cudaHostAllocDefault));
     WFE_CUDA(cudaHostAlloc((void**)&s.h_mask, c * h->n_frames * sizeof(int32_t), cudaHostAllocDefault));
-    WFE_CUDA(cudaHostAlloc((void**)&s.h_off, (c + 1) * sizeof(int64_t), cudaHostAllocDefault));
+    WFE_CUDA(cudaHostAlloc((void**)&s.h_off, 2 * c * sizeof(int64_t), cudaHostAllocDefault));
     WFE_CUDA(cudaMalloc(&s.d_in, in_bytes));
     WFE_CUDA(cudaMalloc((void**)&s.d_out, out_elems * sizeof(float)));
     WFE_CUDA(cudaMalloc((void**)&s.d_mask, c * h->n_frames * sizeof(int32_t)));
-    WFE_CUDA(cudaMalloc((void**)&s.d_off, (c + 1) * sizeof(int64_t)));
+    WFE_CUDA(cudaMalloc((void**)&s.d_off, 2 * c * sizeof(int64_t)));
     WFE_CUDA(cudaMalloc(&s.d_scratch, scratch_bytes(h, (int)c)));
     WFE_CUDA(cudaMalloc((void**)&s.d_stats, c * 2 * sizeof(float)));
   }
@@ -233,40 +253,63 @@ int wfe_create(const wfe_config* cfg, const float* mel_filters, wfe_handle** out
   h->n_frames = cfg->n_samples / wfe::kHop;
   h->ntiles = (h->n_frames + wfe::kTileF - 1) / wfe::kTileF;
 
-  // banded (CSR-by-mel) filter bank; rows index the in-place power buffer
-  std::vector<int2> tab;
-  std::vector<int32_t> start(cfg->n_mel + 1, 0);
-  for (int m = 0; m < cfg->n_mel; ++m) {
-    start[m] = (int32_t)tab.size();
-    for (int k = 0; k < wfe::kBins; ++k) {
-      const float w = mel_filters[(size_t)k * cfg->n_mel + m];
-      if (w != 0.0f) {
-        int2 e;
-        e.x = bin_to_row(k) * wfe::kTileF;
-        memcpy(&e.y, &w, sizeof(float));
-        tab.push_back(e);
-      }
+  if (h->ntiles > wfe::kRing) {
+    delete h;
+    return fail(WFE_ERR_UNSUPPORTED, "n_samples too long: at most 128 tiles of 32 frames (40.96 s) per clip");
+  }
+  h->sm_count = prop.multiProcessorCount;
+
+  // ---- mel projection tables: the filter bank is banded, so only the non-zero 8-mel x 8-bin blocks are kept ----
+  // n-tile j = mels [8j, 8j+8); its k-steps cover bins [lo_j, hi_j] in chunks of 8; B fragments of mma.m16n8k8 (col):
+  //   lane (g = lane/4, t = lane%4): b0 = F[kb+t][8j+g], b1 = F[kb+t+4][8j+g], pre-rounded to TF32.
+  const int n_mel = cfg->n_mel, n_tiles_n = (n_mel + 7) / 8;
+  std::vector<float2> btab;
+  std::vector<wfe::MelUnit> units;
+  auto F = [&](int k, int m) -> float {
+    return (k >= 0 && k < wfe::kBins && m < n_mel) ? mel_filters[(size_t)k * n_mel + m] : 0.0f;
+  };
+  for (int j = 0; j < n_tiles_n; ++j) {
+    int lo = wfe::kBins, hi = -1;
+    for (int k = 0; k < wfe::kBins; ++k)
+      for (int m = 8 * j; m < 8 * j + 8 && m < n_mel; ++m)
+        if (F(k, m) != 0.0f) {
+          lo = k < lo ? k : lo;
+          hi = k > hi ? k : hi;
+        }
+    wfe::MelUnit u;
+    u.kstep0 = (int16_t)(btab.size() / 32);
+    u.nb = (int16_t)(8 * j);
+    if (hi < 0) {  // all-zero filters: one k-step of zeros keeps the epilogue (log10(1e-10)) uniform
+      lo = 0;
+      hi = 0;
     }
+    u.kb = (int16_t)lo;
+    u.ks = (int16_t)((hi - lo + 8) / 8);
+    for (int s = 0; s < u.ks; ++s)
+      for (int lane = 0; lane < 32; ++lane) {
+        const int g = lane >> 2, t = lane & 3, kb = lo + 8 * s;
+        btab.push_back(make_float2(tf32_rna(F(kb + t, 8 * j + g)), tf32_rna(F(kb + t + 4, 8 * j + g))));
+      }
+    units.push_back(u);  // frames  0..15 of the tile
+    units.push_back(u);  // frames 16..31
   }
-  start[cfg->n_mel] = (int32_t)tab.size();
-  h->nnz = (int)tab.size();
-  if (h->nnz > 4096) {
+  h->n_units = (int)units.size();
+  h->n_ksteps = (int)(btab.size() / 32);
+  if (h->n_units > wfe::kMaxUnits || h->n_ksteps > wfe::kMaxKsteps) {
     delete h;
-    return fail(WFE_ERR_UNSUPPORTED, "mel filter bank has more than 4096 non-zeros");
+    return fail(WFE_ERR_UNSUPPORTED, "mel filter bank is not banded enough for the tensor-pipe projection");
   }
-  int rc = upload_constants();
-  if (rc != WFE_OK) {
-    delete h;
-    return rc;
-  }
-  const size_t tab_bytes = (tab.empty() ? 1 : tab.size()) * sizeof(int2);
-  if (cudaMalloc((void**)&h->d_mel_tab, tab_bytes) != cudaSuccess ||
-      cudaMalloc((void**)&h->d_mel_start, start.size() * sizeof(int32_t)) != cudaSuccess) {
+  std::vector<float> s1c(8 * wfe::kS1ConstVec * 4);
+  wfe::fill_stage1_consts(s1c.data());
+  if (cudaMalloc((void**)&h->d_s1_consts, s1c.size() * sizeof(float)) != cudaSuccess ||
+      cudaMalloc((void**)&h->d_mel_btab, btab.size() * sizeof(float2)) != cudaSuccess ||
+      cudaMalloc((void**)&h->d_mel_units, units.size() * sizeof(wfe::MelUnit)) != cudaSuccess) {
     wfe_destroy(h);
-    return fail(WFE_ERR_NOMEM, "cudaMalloc failed for filter tables");
+    return fail(WFE_ERR_NOMEM, "cudaMalloc failed for constant tables");
   }
-  if (!tab.empty()) cudaMemcpy(h->d_mel_tab, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice);
-  cudaMemcpy(h->d_mel_start, start.data(), start.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+  cudaMemcpy(h->d_s1_consts, s1c.data(), s1c.size() * sizeof(float), cudaMemcpyHostToDevice);
+  cudaMemcpy(h->d_mel_btab, btab.data(), btab.size() * sizeof(float2), cudaMemcpyHostToDevice);
+  cudaMemcpy(h->d_mel_units, units.data(), units.size() * sizeof(wfe::MelUnit), cudaMemcpyHostToDevice);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     wfe_destroy(h);
@@ -280,8 +323,9 @@ void wfe_destroy(wfe_handle* h) {
   if (h == nullptr) return;
   DeviceGuard guard(h->cfg.device);
   free_ring(h);
-  if (h->d_mel_tab) cudaFree(h->d_mel_tab);
-  if (h->d_mel_start) cudaFree(h->d_mel_start);
+  if (h->d_s1_consts) cudaFree(h->d_s1_consts);
+  if (h->d_mel_btab) cudaFree(h->d_mel_btab);
+  if (h->d_mel_units) cudaFree(h->d_mel_units);
   delete h;
 }
 
@@ -293,7 +337,8 @@ size_t wfe_logmel_scratch_bytes(const wfe_handle* h, int32_t batch) {
 int32_t wfe_n_frames(const wfe_handle* h) { return h ? h->n_frames : 0; }
 
 int wfe_logmel(wfe_handle* h, const void* pcm, int32_t pcm_dtype, float pcm_scale, const int64_t* offsets,
-               int32_t batch, const float* norm_stats, float* out, int32_t* attn_mask, void* scratch, void* stream) {
+               const int64_t* lengths, int32_t batch, const float* norm_stats, float* out, int32_t* attn_mask,
+               void* scratch, void* stream) {
   if (check_handle(h)) return WFE_ERR_INVALID;
   if (batch < 0) return fail(WFE_ERR_INVALID, "negative batch");
   if (batch == 0) return WFE_OK;
@@ -304,16 +349,16 @@ int wfe_logmel(wfe_handle* h, const void* pcm, int32_t pcm_dtype, float pcm_scal
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (pcm_dtype) {
     case WFE_PCM_F32:
-      return launch_logmel<float>(h, pcm, 1.0f, offsets, batch, norm_stats, out, attn_mask, scratch, st);
+      return launch_logmel<float>(h, pcm, 1.0f, offsets, lengths, batch, norm_stats, out, attn_mask, scratch, st);
     case WFE_PCM_I16:
-      return launch_logmel<int16_t>(h, pcm, pcm_scale, offsets, batch, norm_stats, out, attn_mask, scratch, st);
+      return launch_logmel<int16_t>(h, pcm, pcm_scale, offsets, lengths, batch, norm_stats, out, attn_mask, scratch, st);
     default:
       return fail(WFE_ERR_INVALID, "unknown pcm_dtype");
   }
 }
 
 int wfe_clip_stats(wfe_handle* h, const void* pcm, int32_t pcm_dtype, float pcm_scale, const int64_t* offsets,
-                   int32_t batch, float* stats, void* stream) {
+                   const int64_t* lengths, int32_t batch, float* stats, void* stream) {
   if (check_handle(h)) return WFE_ERR_INVALID;
   if (batch < 0) return fail(WFE_ERR_INVALID, "negative batch");
   if (batch == 0) return WFE_OK;
@@ -322,9 +367,9 @@ int wfe_clip_stats(wfe_handle* h, const void* pcm, int32_t pcm_dtype, float pcm_
   if (!guard.ok) return fail(WFE_ERR_CUDA, "cudaSetDevice failed");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (pcm_dtype == WFE_PCM_F32)
-    wfe::clip_stats_kernel<float><<<batch, 512, 0, st>>>(pcm, 1.0f, offsets, h->cfg.n_samples, reinterpret_cast<float2*>(stats));
+    wfe::clip_stats_kernel<float><<<batch, 512, 0, st>>>(pcm, 1.0f, offsets, lengths, h->cfg.n_samples, reinterpret_cast<float2*>(stats));
   else if (pcm_dtype == WFE_PCM_I16)
-    wfe::clip_stats_kernel<int16_t><<<batch, 512, 0, st>>>(pcm, pcm_scale, offsets, h->cfg.n_samples, reinterpret_cast<float2*>(stats));
+    wfe::clip_stats_kernel<int16_t><<<batch, 512, 0, st>>>(pcm, pcm_scale, offsets, lengths, h->cfg.n_samples, reinterpret_cast<float2*>(stats));
   else
     return fail(WFE_ERR_INVALID, "unknown pcm_dtype");
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -405,62 +450,68 @@ int wfe_extract_host(wfe_handle* h, const void* const* clips, const int64_t* len
     rc = retire_slot(h, s);
     if (rc != WFE_OK) return rc;
     const int n = (batch - c0 < chunk) ? batch - c0 : chunk;
-    // ragged pack: only min(len, n_samples) samples of each clip cross PCIe
-    int64_t pos = 0;
+    // ragged pack: only min(len, n_samples) samples of each clip cross PCIe; every clip starts on a 16-byte boundary
+    // of the device buffer so that the kernel's 128-bit load path applies (starts in h_off[0..n), lengths after them)
+    int64_t* starts = s.h_off;
+    int64_t* lens = s.h_off + chunk;
+    int64_t pos = 0, payload = 0;
     for (int i = 0; i < n; ++i) {
-      s.h_off[i] = pos;
       int64_t len = lengths[c0 + i];
       if (len < 0) return fail(WFE_ERR_INVALID, "negative clip length");
       if (len > h->cfg.n_samples) len = h->cfg.n_samples;
       if (len > 0 && clips[c0 + i] == nullptr) return fail(WFE_ERR_INVALID, "null clip pointer");
-      pos += len;
+      starts[i] = pos;
+      lens[i] = len;
+      payload += len;
+      pos = (pos + len + 7) & ~(int64_t)7;
     }
-    s.h_off[n] = pos;
     // contiguous runs of pinned clips go straight from the caller's memory; everything else is staged
     int i = 0;
     while (i < n) {
-      const int64_t len_i = s.h_off[i + 1] - s.h_off[i];
-      if (len_i == 0) {
+      if (lens[i] == 0) {
         ++i;
         continue;
       }
       const char* src = static_cast<const char*>(clips[c0 + i]);
       if (is_pinned_host(src)) {
+        // extend the run while the next clip continues the source exactly where the device layout expects it
         int j = i + 1;
-        int64_t run = len_i;
-        while (j < n && static_cast<const char*>(clips[c0 + j]) == src + (size_t)run * es &&
-               lengths[c0 + j - 1] <= h->cfg.n_samples) {
-          run += s.h_off[j + 1] - s.h_off[j];
+        while (j < n && lens[j] > 0 &&
+               static_cast<const char*>(clips[c0 + j]) == src + (size_t)(starts[j] - starts[i]) * es &&
+               starts[j] == starts[j - 1] + lens[j - 1])
           ++j;
-        }
-        WFE_CUDA(cudaMemcpyAsync(static_cast<char*>(s.d_in) + (size_t)s.h_off[i] * es, src, (size_t)run * es,
+        const int64_t run = starts[j - 1] + lens[j - 1] - starts[i];
+        WFE_CUDA(cudaMemcpyAsync(static_cast<char*>(s.d_in) + (size_t)starts[i] * es, src, (size_t)run * es,
                                  cudaMemcpyHostToDevice, s.stream));
         i = j;
       } else {
-        // stage a maximal run of pageable clips, then one H2D for the run
+        // stage a maximal run of pageable clips, then one H2D for the run (alignment gaps travel too: < 32 B each)
         const int i0 = i;
-        while (i < n && !(s.h_off[i + 1] > s.h_off[i] && is_pinned_host(clips[c0 + i]))) {
-          const int64_t l = s.h_off[i + 1] - s.h_off[i];
-          if (l > 0) memcpy(static_cast<char*>(s.h_in) + (size_t)s.h_off[i] * es, clips[c0 + i], (size_t)l * es);
+        int last = i;
+        while (i < n && !(lens[i] > 0 && is_pinned_host(clips[c0 + i]))) {
+          if (lens[i] > 0) {
+            memcpy(static_cast<char*>(s.h_in) + (size_t)starts[i] * es, clips[c0 + i], (size_t)lens[i] * es);
+            last = i;
+          }
           ++i;
         }
-        const size_t bytes = (size_t)(s.h_off[i] - s.h_off[i0]) * es;
+        const size_t bytes = (size_t)(starts[last] + lens[last] - starts[i0]) * es;
         if (bytes)
-          WFE_CUDA(cudaMemcpyAsync(static_cast<char*>(s.d_in) + (size_t)s.h_off[i0] * es,
-                                   static_cast<char*>(s.h_in) + (size_t)s.h_off[i0] * es, bytes,
-                                   cudaMemcpyHostToDevice, s.stream));
+          WFE_CUDA(cudaMemcpyAsync(static_cast<char*>(s.d_in) + (size_t)starts[i0] * es,
+                                   static_cast<char*>(s.h_in) + (size_t)starts[i0] * es, bytes, cudaMemcpyHostToDevice,
+                                   s.stream));
       }
     }
-    up += (uint64_t)pos * es + (uint64_t)(n + 1) * sizeof(int64_t);
-    WFE_CUDA(cudaMemcpyAsync(s.d_off, s.h_off, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s.stream));
+    up += (uint64_t)payload * es + (uint64_t)(2 * n) * sizeof(int64_t);
+    WFE_CUDA(cudaMemcpyAsync(s.d_off, s.h_off, (size_t)(2 * chunk) * sizeof(int64_t), cudaMemcpyHostToDevice, s.stream));
     const float* stats = nullptr;
     if (do_normalize) {
-      rc = wfe_clip_stats(h, s.d_in, pcm_dtype, pcm_scale, s.d_off, n, s.d_stats, s.stream);
+      rc = wfe_clip_stats(h, s.d_in, pcm_dtype, pcm_scale, s.d_off, s.d_off + chunk, n, s.d_stats, s.stream);
       if (rc != WFE_OK) return rc;
       stats = s.d_stats;
     }
-    rc = wfe_logmel(h, s.d_in, pcm_dtype, pcm_scale, s.d_off, n, stats, s.d_out, attn_mask ? s.d_mask : nullptr,
-                    s.d_scratch, s.stream);
+    rc = wfe_logmel(h, s.d_in, pcm_dtype, pcm_scale, s.d_off, s.d_off + chunk, n, stats, s.d_out,
+                    attn_mask ? s.d_mask : nullptr, s.d_scratch, s.stream);
     if (rc != WFE_OK) return rc;
     float* dst = out + (size_t)c0 * clip_out;
     if (out_pinned) {

@@ -1,22 +1,24 @@
-// Whisper log-mel frontend kernels for sm_100a (B200).
+// Whisper log-mel frontend kernel for sm_100a (B200): ONE persistent kernel per batch.
 //
-// One CTA = one tile of 32 consecutive STFT frames of one clip; LANE == FRAME everywhere, so every
-// shared-memory access is [row][lane] (stride-1 across the warp, conflict-free), every twiddle /
-// window / mel weight is warp-uniform, and no shuffles or divergent branches are needed.
+// Unit of work = a tile of 32 consecutive STFT frames of one clip; LANE == FRAME in the FFT stages, so every
+// shared-memory access is [row][lane] (conflict-free) and every constant is warp-uniform.  CTAs are persistent
+// (grid = SMs x resident CTAs) and pull tile ids from a global counter, clip-major.
 //
-//   stage 0  coalesced 128-bit loads of the tile's 5360 PCM samples -> smem, applying truncate /
-//            right-zero-pad to n_samples and the centred reflect pad            (Appendix A steps 2-3)
-//   stage 1  16 tasks (n1): Hann window + real 25-point DFT (5x5) over samples n1+16*n2, then the
-//            W400^(n1*k2) twiddle                                                (steps 5-6)
-//   stage 2  13 tasks (k2): complex 16-point DFT (4x4) over n1 -> bins 25*k1+k2 (folded to 0..200 by
-//            conjugate symmetry), power |X|^2 stored in place                    (steps 6-7)
-//   stage 3  n_mel tasks: banded slaney mel projection (fp32 FFMA, <=2 non-zeros per bin), log10,
-//            (x+4)/4, coalesced store, per-clip running max                      (steps 8, 9, 11)
-//   stage 4  the LAST tile of a clip to finish applies the per-clip max-8 clamp to the (L2-resident)
-//            tiles that need it                                                  (step 10)
+//   stage 0  coalesced 128-bit loads of the tile's 5360 PCM samples -> smem (truncate / right-zero-pad to n_samples,
+//            centred reflect pad, optional int16 -> float and zero-mean/unit-variance)          (Appendix A steps 2-3)
+//   stage 1  8 warps x (n1, n1+1): Hann window, real 25-point DFT (5x5), W400^(n1 k2) twiddle -- two n1 per thread,
+//            packed f32x2 (FADD2/FMUL2/FFMA2)                                                    (steps 5-6)
+//   stage 2  6 warps x (k2, k2+1) + 1 warp for k2 = 0: complex 16-point DFT (4x4) over n1, power |X|^2, stored
+//            bin-major                                                                           (steps 6-7)
+//   stage 3  mel projection on the tensor pipe: the slaney filter bank is banded (33 non-zero 8-mel x 8-bin blocks of
+//            26 x 16), so each warp issues a handful of mma.sync m16n8k8 TF32 (frames x bins x mels) with the filter
+//            fragments read from smem; epilogue log10, (x+4)/4, store, tile min/max              (steps 8, 9, 11)
+//   clamp    per-clip max-8 clamp (step 10) without a second pass over HBM: every CTA remembers its own tiles and,
+//            once the clip's ticket shows all of its tiles are done, re-reads only the tiles whose minimum is below
+//            the floor from L2 and fixes them; tiles that lie entirely in the zero padding are written once, late.
 //
-// Arithmetic restated from HF:models/whisper/feature_extraction_whisper.py:135-164 (see SURVEY.md
-// Appendix A); 400 = 16 x 25 Cooley-Tukey: n = n1 + 16*n2, k = k2 + 25*k1,
+// Arithmetic restated from HF:models/whisper/feature_extraction_whisper.py:135-164;
+// 400 = 16 x 25 Cooley-Tukey: n = n1 + 16*n2, k = k2 + 25*k1,
 //   X[k2+25k1] = sum_n1 W16^(n1 k1) * W400^(n1 k2) * sum_n2 x[n1+16 n2] W25^(n2 k2).
 #pragma once
 #include <cuda_runtime.h>
@@ -28,12 +30,18 @@ namespace wfe {
 
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
-constexpr int kSigLen = (kTileF - 1) * kHop + kNFft;      // 5360 padded-signal samples per tile
-constexpr int kSigSm = kSigLen + kSigLen / kHop + 2;      // +1 pad word per 160 samples (bank skew)
-constexpr int kZRows = 400;                               // intermediate rows per frame
-constexpr size_t kSmemBytes = (size_t)(kSigSm + kZRows * kTileF) * sizeof(float);
+constexpr int kSigLen = (kTileF - 1) * kHop + kNFft;  // 5360 padded-signal samples per tile
+constexpr int kSigStride = kHop + 2;                  // +2 pad words per 160 samples: conflict-free LDS.64 across frames
+constexpr int kSigSm = kSigLen + 2 * (kSigLen / kHop) + 4;
+constexpr int kBufA = kPRows * kPStride;              // power buffer (also the signal staging area): 8320 floats
+constexpr int kZSm = kZPlanes * 16 * kTileF;          // 12800 floats
+constexpr int kRing = 128;                            // pending-tile ring (>= tiles per clip, see wfe_api.cu)
+constexpr int kMaxUnits = 64;                         // (8-mel tile, 16-frame tile) work units of the mel stage
+constexpr int kMaxKsteps = 64;                        // non-zero 8x8 blocks of the filter bank (33 for Whisper)
 
-// order-preserving float <-> uint32 key (for atomicMax on floats of either sign); key 0 < every float
+static_assert(kSigSm <= kBufA, "signal staging must fit in the power buffer");
+
+// order-preserving float <-> uint32 key (for atomic max on floats of either sign); key 0 < every float
 __device__ __forceinline__ uint32_t f2key(float f) {
   const uint32_t u = __float_as_uint(f);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
@@ -49,181 +57,382 @@ __device__ __forceinline__ float pcm_to_float<float>(float v, float) { return v;
 template <>
 __device__ __forceinline__ float pcm_to_float<int16_t>(int16_t v, float scale) { return (float)v * scale; }
 
+// one mel-stage work unit: 8 mels x 16 frames, `ks` k-steps of 8 bins starting at bin `kb`
+struct MelUnit {
+  int16_t kstep0;  // first k-step (index into the B-fragment table)
+  int16_t ks;      // number of k-steps
+  int16_t kb;      // first bin
+  int16_t nb;      // first mel
+};
+
 struct LogmelParams {
   const void* pcm;
-  const int64_t* offsets;
-  const float2* norm;      // (mean, rstd) per clip or nullptr
-  float* out;              // (B, n_mel, n_frames)
-  int32_t* mask;           // (B, n_frames) or nullptr
-  uint32_t* clip_key;      // [B] running max of log2(mel) as ordered key (zero-initialised)
-  uint32_t* clip_ticket;   // [B] finished-tile counter (zero-initialised)
-  float* tile_min;         // [B * ntiles]
-  const int2* mel_tab;     // nnz entries: (row*32, float bits of weight), grouped by mel
-  const int32_t* mel_start;  // [n_mel + 1]
+  const int64_t* offsets;   // [B+1] (or [B] when lengths != nullptr)
+  const int64_t* lengths;   // [B] or nullptr
+  const float2* norm;       // (mean, rstd) per clip or nullptr
+  float* out;               // (B, n_mel, n_frames)
+  int32_t* mask;            // (B, n_frames) or nullptr
+  uint32_t* clip_key;       // [B] running max of log10(mel) as ordered key (zero-initialised)
+  uint32_t* clip_ticket;    // [B] finished-tile counter (zero-initialised)
+  uint32_t* tile_counter;   // [1] dynamic tile scheduler (zero-initialised)
+  const float4* s1_consts;  // [8][25] per-warp window/twiddle block
+  const float2* mel_btab;   // [n_ksteps][32] per-lane B fragments (TF32-rounded filter weights)
+  const MelUnit* mel_units; // [n_units]
   float pcm_scale;
-  int n_mel, n_samples, n_frames, ntiles;
+  int n_mel, n_samples, n_frames, ntiles, n_units, n_ksteps;
+  uint32_t total_tiles;
 };
+
+__host__ __device__ inline size_t logmel_smem_bytes(int n_ksteps) {
+  return (size_t)(kBufA + kZSm) * 4 + 8 * kS1ConstVec * 16 + (size_t)n_ksteps * 32 * 8;
+}
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_max_u32(uint32_t* p, uint32_t v) {
+  asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_release_add_u32(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t f32_to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// log10(max(v, 1e-10)); exactly -10 on the clamp so that silence is bit-identical to the reference (-1.5 after scaling)
+__device__ __forceinline__ float log10_clamped(float v) { return v > 1e-10f ? lg2_approx(v) * kLog10_2 : -10.0f; }
+
+struct FixEntry {
+  int b, tile;       // tile < 0: nothing to do
+  float floor_y;     // ((g - 8) + 4) / 4
+  int silent;        // tile lies in the zero padding: store the constant instead of clamping
+};
+
+// apply the per-clip clamp to one of this CTA's own tiles (values come back from L2)
+__device__ __forceinline__ void fix_tile(const LogmelParams& p, const FixEntry& fx, int warp, int lane) {
+  const int t0 = fx.tile * kTileF;
+  if (t0 + lane >= p.n_frames) return;
+  float* q = p.out + ((size_t)fx.b * p.n_mel) * p.n_frames + t0 + lane;
+  if (fx.silent) {
+    const float y = fmaxf(-1.5f, fx.floor_y);  // (max(-10, g-8) + 4) / 4
+    for (int m = warp; m < p.n_mel; m += kWarps) q[(size_t)m * p.n_frames] = y;
+  } else {
+    for (int m0 = warp; m0 < p.n_mel; m0 += 4 * kWarps) {
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int m = m0 + j * kWarps;
+        v[j] = m < p.n_mel ? __ldcg(q + (size_t)m * p.n_frames) : 3.0e38f;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int m = m0 + j * kWarps;
+        if (v[j] < fx.floor_y) q[(size_t)m * p.n_frames] = fx.floor_y;
+      }
+    }
+  }
+}
+
+__device__ __noinline__ void fix_tile_serial(const LogmelParams& p, const FixEntry fx) {
+  const int t0 = fx.tile * kTileF;
+  const int nv = min(kTileF, p.n_frames - t0);
+  float* q = p.out + ((size_t)fx.b * p.n_mel) * p.n_frames + t0;
+  const float ys = fmaxf(-1.5f, fx.floor_y);
+  for (int m = 0; m < p.n_mel; ++m)
+    for (int f = 0; f < nv; ++f) {
+      float* e = q + (size_t)m * p.n_frames + f;
+      if (fx.silent)
+        *e = ys;
+      else if (__ldcg(e) < fx.floor_y)
+        *e = fx.floor_y;
+    }
+}
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams p) {
   extern __shared__ __align__(16) float smem[];
-  float* sig = smem;
-  float* zbuf = smem + kSigSm;
+  float* const bufA = smem;                 // signal staging (stage 0-1), then power (stage 2-3)
+  float* const zbuf = smem + kBufA;
+  float4* const s_cst = reinterpret_cast<float4*>(zbuf + kZSm);
+  float2* const s_btab = reinterpret_cast<float2*>(s_cst + 8 * kS1ConstVec);
+  __shared__ MelUnit s_units[kMaxUnits];
   __shared__ float s_red[2][kWarps];
-  __shared__ int s_last;
+  __shared__ uint32_t s_next[2];
+  __shared__ FixEntry s_fix[2];
+  __shared__ int s_pend_bt[kRing];     // b * ntiles + tile  (tile id)
+  __shared__ float s_pend_min[kRing];  // tile minimum of y; -inf marks a silent (not yet written) tile
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b = blockIdx.x / p.ntiles, tile = blockIdx.x - b * p.ntiles;
-  const int t0 = tile * kTileF;
-  const int64_t off = p.offsets[b];
-  const int64_t avail = p.offsets[b + 1] - off;
-  const int len = (int)(avail < (int64_t)p.n_samples ? avail : (int64_t)p.n_samples);   // truncate to 30 s
-  const int s_begin = t0 * kHop - kNFft / 2;   // unpadded sample index of sig[0]
-  const int nvalid = min(kTileF, p.n_frames - t0);
-  float* const out_tile = p.out + ((size_t)b * p.n_mel) * p.n_frames + t0;
 
-  if (p.mask != nullptr && tid < nvalid) p.mask[(size_t)b * p.n_frames + t0 + tid] = ((t0 + tid) * kHop < len) ? 1 : 0;
+  // ---- one-time CTA set-up: constant blocks to smem, zero the k-padding rows of the power buffer ----
+  for (int i = tid; i < 8 * kS1ConstVec; i += kThreads) s_cst[i] = p.s1_consts[i];
+  for (int i = tid; i < p.n_ksteps * 32; i += kThreads) s_btab[i] = p.mel_btab[i];
+  for (int i = tid; i < p.n_units; i += kThreads) s_units[i] = p.mel_units[i];
+  for (int i = tid; i < (kPRows - kBins) * kPStride; i += kThreads) bufA[kBins * kPStride + i] = 0.f;
+  // frames >= 32 columns of the stride-40 rows are never read; no need to clear them
+  if (tid == 0) {
+    s_next[0] = atomicAdd(p.tile_counter, 1u);
+    s_fix[0].tile = -1;
+    s_fix[1].tile = -1;
+  }
+  __syncthreads();
 
-  // lowest source sample this tile touches (right reflect maps s >= n_samples to 2(n-1)-s)
-  const int s_hi = s_begin + kSigLen - 1;
-  int lowest = s_begin < 0 ? 0 : s_begin;
-  if (s_hi >= p.n_samples) lowest = min(lowest, 2 * (p.n_samples - 1) - s_hi);
-  const bool silent = lowest >= len;   // every sample of every frame in the tile is zero padding
+  // pending ring state lives in thread 0's registers
+  int ring_head = 0, ring_count = 0;
+  uint32_t cur = s_next[0];
+  int parity = 0;
 
-  float tmax_lg = -3.0e38f, tmin_y = 3.0e38f;
-  if (silent) {
-    // mel == 0 exactly -> log10(1e-10) path; no FFT needed
-    const float lg = __log2f(1e-10f);
-    const float y = fmaf(lg, 0.25f * kLog10_2, 1.0f);
-    for (int i = tid; i < p.n_mel * kTileF; i += kThreads) {
-      const int m = i >> 5, f = i & 31;
-      if (f < nvalid) out_tile[(size_t)m * p.n_frames + f] = y;
+  while (cur < p.total_tiles) {
+    const int b = (int)(cur / (uint32_t)p.ntiles), tile = (int)(cur - (uint32_t)b * (uint32_t)p.ntiles);
+    const int t0 = tile * kTileF;
+    const int64_t off = p.offsets[b];
+    const int64_t avail = (p.lengths != nullptr ? p.lengths[b] : p.offsets[b + 1] - off);
+    const int len = (int)(avail < (int64_t)p.n_samples ? avail : (int64_t)p.n_samples);  // truncate to 30 s
+    const int s_begin = t0 * kHop - kNFft / 2;  // unpadded sample index of sig[0]
+    const int nvalid = min(kTileF, p.n_frames - t0);
+
+    // thread 0: prefetch the next tile id and the tickets of the two oldest pending tiles (consumed much later)
+    uint32_t next_reg = 0, tk0 = 0, tk1 = 0;
+    int pb0 = -1, pb1 = -1;
+    if (tid == 0) {
+      next_reg = atomicAdd(p.tile_counter, 1u);
+      if (ring_count > 0) {
+        pb0 = s_pend_bt[ring_head] / p.ntiles;
+        tk0 = ld_acquire_u32(p.clip_ticket + pb0);
+      }
+      if (ring_count > 1) {
+        pb1 = s_pend_bt[(ring_head + 1) & (kRing - 1)] / p.ntiles;
+        tk1 = ld_acquire_u32(p.clip_ticket + pb1);
+      }
     }
-    tmax_lg = lg;
-    tmin_y = y;
-  } else {
-    // ---- stage 0: PCM -> smem (skewed), with zero pad / reflect pad / optional normalisation ----
-    const T* pcm = reinterpret_cast<const T*>(p.pcm) + off;
-    float mean = 0.f, rstd = 1.f;
-    if (p.norm != nullptr) {
-      const float2 st = p.norm[b];
-      mean = st.x;
-      rstd = st.y;
-    }
-    const bool interior = (s_begin >= 0) && (s_begin + kSigLen <= len);
-    constexpr int kVec = 16 / (int)sizeof(T);
-    if (interior) {
-      const T* src = pcm + s_begin;
-      const int mis = (int)((reinterpret_cast<uintptr_t>(src) / sizeof(T)) % kVec);
-      const int head = (kVec - mis) % kVec;
-      const int nvec = (kSigLen - head) / kVec;
-      for (int i = tid; i < head; i += kThreads) sig[i + i / kHop] = (pcm_to_float<T>(src[i], p.pcm_scale) - mean) * rstd;
-      const uint4* src4 = reinterpret_cast<const uint4*>(src + head);
-      for (int v = tid; v < nvec; v += kThreads) {
-        const uint4 raw = __ldg(src4 + v);
-        const T* e = reinterpret_cast<const T*>(&raw);
+
+    if (p.mask != nullptr && tid < nvalid) p.mask[(size_t)b * p.n_frames + t0 + tid] = ((t0 + tid) * kHop < len) ? 1 : 0;
+
+    // lowest source sample this tile touches (right reflect maps s >= n_samples to 2(n-1)-s)
+    const int s_hi = s_begin + kSigLen - 1;
+    int lowest = s_begin < 0 ? 0 : s_begin;
+    if (s_hi >= p.n_samples) lowest = min(lowest, 2 * (p.n_samples - 1) - s_hi);
+    const bool silent = lowest >= len;  // every sample of every frame in the tile is zero padding
+
+    float tmax_l10 = -10.0f, tmin_y = 3.0e38f;
+    if (!silent) {
+      // ---- stage 0: PCM -> smem (skewed), with zero pad / reflect pad / optional normalisation ----
+      const T* pcm = reinterpret_cast<const T*>(p.pcm) + off;
+      float mean = 0.f, rstd = 1.f;
+      if (p.norm != nullptr) {
+        const float2 st = p.norm[b];
+        mean = st.x;
+        rstd = st.y;
+      }
+      constexpr int kVec = 16 / (int)sizeof(T);  // samples per 128-bit load
+      const bool fast = (s_begin >= 0) && (s_begin + kSigLen <= len) &&
+                        ((reinterpret_cast<uintptr_t>(pcm + s_begin) & 15u) == 0);
+      if (fast) {
+        const uint4* src4 = reinterpret_cast<const uint4*>(pcm + s_begin);
+#pragma unroll 2
+        for (int v = tid; v < kSigLen / kVec; v += kThreads) {
+          const uint4 raw = __ldg(src4 + v);
+          const T* e = reinterpret_cast<const T*>(&raw);
+          const int i = v * kVec;
+          float* dst = bufA + i + 2 * (i / kHop);  // 160 is a multiple of kVec: a vector never straddles a hop row
 #pragma unroll
-        for (int j = 0; j < kVec; ++j) {
-          const int i = head + v * kVec + j;
-          sig[i + i / kHop] = (pcm_to_float<T>(e[j], p.pcm_scale) - mean) * rstd;
+          for (int j = 0; j < kVec; j += 2) {
+            float2 o;
+            o.x = (pcm_to_float<T>(e[j], p.pcm_scale) - mean) * rstd;
+            o.y = (pcm_to_float<T>(e[j + 1], p.pcm_scale) - mean) * rstd;
+            *reinterpret_cast<float2*>(dst + j) = o;
+          }
+        }
+      } else {
+        for (int i = tid; i < kSigLen; i += kThreads) {
+          int s = s_begin + i;
+          if (s < 0) s = -s;
+          if (s >= p.n_samples) s = 2 * (p.n_samples - 1) - s;
+          float v = 0.f;
+          if (s >= 0 && s < len) v = (pcm_to_float<T>(pcm[s], p.pcm_scale) - mean) * rstd;
+          bufA[i + 2 * (i / kHop)] = v;
         }
       }
-      for (int i = head + nvec * kVec + tid; i < kSigLen; i += kThreads)
-        sig[i + i / kHop] = (pcm_to_float<T>(src[i], p.pcm_scale) - mean) * rstd;
-    } else {
-      for (int i = tid; i < kSigLen; i += kThreads) {
-        int s = s_begin + i;
-        if (s < 0) s = -s;
-        if (s >= p.n_samples) s = 2 * (p.n_samples - 1) - s;
-        float v = 0.f;
-        if (s >= 0 && s < len) v = (pcm_to_float<T>(pcm[s], p.pcm_scale) - mean) * rstd;
-        sig[i + i / kHop] = v;
-      }
     }
-    __syncthreads();
+    if (tid == 0) s_next[parity ^ 1] = next_reg;
+    __syncthreads();  // S1: signal staged; s_next and s_fix (from the previous tile's bookkeeping) published
 
-    // ---- stage 1 ----
-    {
-      const float* sig_lane = sig + (kHop + 1) * lane;
-      float* zcol = zbuf + lane;
-      for (int n1 = warp; n1 < 16; n1 += kWarps) stage1_task(sig_lane, n1, zcol);
-    }
-    __syncthreads();
-    // ---- stage 2 ----
-    for (int k2 = warp; k2 < 13; k2 += kWarps) stage2_task(zbuf + lane, k2);
-    __syncthreads();
-    // ---- stage 3: banded mel + log + scale ----
-    const bool lane_ok = lane < nvalid;
-    for (int m = warp; m < p.n_mel; m += kWarps) {
-      const int e0 = __ldg(p.mel_start + m), e1 = __ldg(p.mel_start + m + 1);
-      float acc = 0.f;
-      for (int e = e0; e < e1; ++e) {
-        const int2 ent = __ldg(p.mel_tab + e);
-        acc = fmaf(__int_as_float(ent.y), zbuf[ent.x + lane], acc);
-      }
-      const float lg = __log2f(fmaxf(acc, 1e-10f));
-      const float y = fmaf(lg, 0.25f * kLog10_2, 1.0f);
-      if (lane_ok) {
-        out_tile[(size_t)m * p.n_frames + lane] = y;
-        tmax_lg = fmaxf(tmax_lg, lg);
-        tmin_y = fminf(tmin_y, y);
-      }
-    }
-  }
-
-  // ---- tile max / min -> clip running max; last tile of the clip applies the clamp ----
+    // ---- clamp fix-ups decided at the end of the previous tile (own tiles, L2-resident) ----
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    tmax_lg = fmaxf(tmax_lg, __shfl_xor_sync(0xffffffffu, tmax_lg, o));
-    tmin_y = fminf(tmin_y, __shfl_xor_sync(0xffffffffu, tmin_y, o));
-  }
-  if (lane == 0) {
-    s_red[0][warp] = tmax_lg;
-    s_red[1][warp] = tmin_y;
-  }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    float mx = s_red[0][0], mn = s_red[1][0];
-#pragma unroll
-    for (int w = 1; w < kWarps; ++w) {
-      mx = fmaxf(mx, s_red[0][w]);
-      mn = fminf(mn, s_red[1][w]);
+    for (int f = 0; f < 2; ++f) {
+      const FixEntry fx = s_fix[f];
+      if (fx.tile >= 0) fix_tile(p, fx, warp, lane);
     }
-    atomicMax(p.clip_key + b, f2key(mx));
-    p.tile_min[(size_t)b * p.ntiles + tile] = mn;
-    __threadfence();
-    const uint32_t ticket = atomicAdd(p.clip_ticket + b, 1u);
-    s_last = (ticket == (uint32_t)p.ntiles - 1u);
-  }
-  __syncthreads();
-  if (!s_last) return;
 
-  // ---- stage 4 (one CTA per clip): out = max(out, ((g - 8) + 4) / 4), g = log10 of the clip max ----
-  __threadfence();
-  const float g = key2f(__ldcg(p.clip_key + b)) * kLog10_2;
-  const float floor_y = ((g - 8.0f) + 4.0f) * 0.25f;
-  float* const out_clip = p.out + ((size_t)b * p.n_mel) * p.n_frames;
-  for (int tt = 0; tt < p.ntiles; ++tt) {
-    if (__ldcg(p.tile_min + (size_t)b * p.ntiles + tt) >= floor_y) continue;   // uniform across the CTA
-    const int nv = min(kTileF, p.n_frames - tt * kTileF);
-    for (int i = tid; i < p.n_mel * kTileF; i += kThreads) {
-      const int m = i >> 5, f = i & 31;
-      if (f < nv) {
-        float* q = out_clip + (size_t)m * p.n_frames + tt * kTileF + f;
-        if (__ldcg(q) < floor_y) *q = floor_y;
+    if (!silent) {
+      // ---- stage 1: warp w owns n1 = 2w, 2w+1 ----
+      stage1_pair(bufA + kSigStride * lane, s_cst + warp * kS1ConstVec, 2 * warp, zbuf + lane);
+      __syncthreads();  // S2
+      // ---- stage 2: warps 0..5 own (k2, k2+1) = (1,2)..(11,12); warp 6 owns k2 = 0 ----
+      if (warp < 6)
+        stage2_pair(zbuf + lane, 2 * warp + 1, bufA + lane);
+      else if (warp == 6)
+        stage2_k0(zbuf + lane, bufA + lane);
+      __syncthreads();  // S3
+      // ---- stage 3: banded mel projection with mma.sync TF32, epilogue log10 / scale / store ----
+      {
+        const int g = lane >> 2, t = lane & 3;
+        float* const out_tile = p.out + ((size_t)b * p.n_mel) * p.n_frames + t0;
+        for (int u = warp; u < p.n_units; u += kWarps) {
+          const MelUnit mu = s_units[u];
+          const int mt = u & 1 ? 16 : 0;  // units come in (frame-half 0, frame-half 1) pairs per mel tile
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+          const float* arow = bufA + (mu.kb + t) * kPStride + mt + g;
+          const float2* brow = s_btab + (int)mu.kstep0 * 32 + lane;
+          for (int s = 0; s < mu.ks; ++s) {
+            uint32_t a[4];
+            a[0] = f32_to_tf32(arow[0]);
+            a[1] = f32_to_tf32(arow[8]);
+            a[2] = f32_to_tf32(arow[4 * kPStride]);
+            a[3] = f32_to_tf32(arow[4 * kPStride + 8]);
+            const float2 bw = *brow;
+            mma_tf32_16x8x8(acc, a, __float_as_uint(bw.x), __float_as_uint(bw.y));
+            arow += 8 * kPStride;
+            brow += 32;
+          }
+          // c0: (frame mt+g, mel nb+2t)  c1: (mt+g, nb+2t+1)  c2: (mt+g+8, nb+2t)  c3: (mt+g+8, nb+2t+1)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int fr = mt + g + (c >> 1) * 8, m = mu.nb + 2 * t + (c & 1);
+            const float l10 = log10_clamped(acc[c]);
+            const float y = (l10 + 4.0f) * 0.25f;
+            if (fr < nvalid && m < p.n_mel) {
+              out_tile[(size_t)m * p.n_frames + fr] = y;
+              tmax_l10 = fmaxf(tmax_l10, l10);
+              tmin_y = fminf(tmin_y, y);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        tmax_l10 = fmaxf(tmax_l10, __shfl_xor_sync(0xffffffffu, tmax_l10, o));
+        tmin_y = fminf(tmin_y, __shfl_xor_sync(0xffffffffu, tmin_y, o));
+      }
+      if (lane == 0) {
+        s_red[0][warp] = tmax_l10;
+        s_red[1][warp] = tmin_y;
       }
     }
+    __syncthreads();  // S4: tile written (visible to this CTA), smem free for the next tile
+
+    // ---- thread 0: publish the tile (clip max, ticket), remember it, decide the next fix-ups ----
+    if (tid == 0) {
+      float mx = -10.0f, mn = -__int_as_float(0x7f800000);  // silent: max = log10(1e-10), min marker = -inf
+      if (!silent) {
+        mx = s_red[0][0];
+        mn = s_red[1][0];
+#pragma unroll
+        for (int w = 1; w < kWarps; ++w) {
+          mx = fmaxf(mx, s_red[0][w]);
+          mn = fminf(mn, s_red[1][w]);
+        }
+      }
+      red_max_u32(p.clip_key + b, f2key(mx));
+      red_release_add_u32(p.clip_ticket + b, 1u);
+      // decide fix-ups for the (up to two) oldest pending tiles from the tickets read at the top of this tile
+      int nfix = 0;
+      if (pb0 >= 0 && tk0 == (uint32_t)p.ntiles) {
+        const float gmax = key2f(__ldcg(p.clip_key + pb0));
+        const float floor_y = ((gmax - 8.0f) + 4.0f) * 0.25f;
+        const int bt = s_pend_bt[ring_head];
+        const float pm = s_pend_min[ring_head];
+        ring_head = (ring_head + 1) & (kRing - 1);
+        --ring_count;
+        if (pm < floor_y) s_fix[nfix++] = FixEntry{pb0, bt - pb0 * p.ntiles, floor_y, pm == -__int_as_float(0x7f800000)};
+        if (pb1 >= 0 && tk1 == (uint32_t)p.ntiles) {
+          const float gmax1 = key2f(__ldcg(p.clip_key + pb1));
+          const float floor1 = ((gmax1 - 8.0f) + 4.0f) * 0.25f;
+          const int bt1 = s_pend_bt[ring_head];
+          const float pm1 = s_pend_min[ring_head];
+          ring_head = (ring_head + 1) & (kRing - 1);
+          --ring_count;
+          if (pm1 < floor1)
+            s_fix[nfix++] = FixEntry{pb1, bt1 - pb1 * p.ntiles, floor1, pm1 == -__int_as_float(0x7f800000)};
+        }
+      }
+      for (int f = nfix; f < 2; ++f) s_fix[f].tile = -1;
+      // push this tile.  The ring holds >= one clip's worth of tiles (host enforces ntiles <= kRing), so a full ring
+      // means the oldest entry's clip has every tile assigned to a RUNNING CTA (tile ids are handed out in order) and
+      // the wait below terminates; this is a never-in-practice path, so thread 0 fixes that tile on its own.
+      if (ring_count == kRing) {
+        const int bt = s_pend_bt[ring_head];
+        const float pm = s_pend_min[ring_head];
+        const int ob = bt / p.ntiles;
+        ring_head = (ring_head + 1) & (kRing - 1);
+        --ring_count;
+        while (ld_acquire_u32(p.clip_ticket + ob) != (uint32_t)p.ntiles) __nanosleep(200);
+        const float gm = key2f(__ldcg(p.clip_key + ob));
+        const float fl = ((gm - 8.0f) + 4.0f) * 0.25f;
+        if (pm < fl) fix_tile_serial(p, FixEntry{ob, bt - ob * p.ntiles, fl, pm == -__int_as_float(0x7f800000)});
+      }
+      const int slot = (ring_head + ring_count) & (kRing - 1);
+      s_pend_bt[slot] = (int)cur;
+      s_pend_min[slot] = mn;
+      ++ring_count;
+    }
+    parity ^= 1;
+    cur = s_next[parity];  // published at S1 of this iteration
+  }
+
+  // ---- drain: the tiles this CTA still has pending; every remaining tile of their clips is owned by a running CTA ----
+  __syncthreads();  // publishes the fix-ups decided by the last tile's bookkeeping
+#pragma unroll
+  for (int f = 0; f < 2; ++f) {
+    const FixEntry fx = s_fix[f];
+    if (fx.tile >= 0) fix_tile(p, fx, warp, lane);
+  }
+  __syncthreads();
+  for (;;) {
+    if (tid == 0) {
+      s_fix[0].tile = -2;  // -2: ring empty
+      if (ring_count > 0) {
+        const int bt = s_pend_bt[ring_head];
+        const float pm = s_pend_min[ring_head];
+        const int ob = bt / p.ntiles;
+        ring_head = (ring_head + 1) & (kRing - 1);
+        --ring_count;
+        while (ld_acquire_u32(p.clip_ticket + ob) != (uint32_t)p.ntiles) __nanosleep(100);
+        const float gm = key2f(__ldcg(p.clip_key + ob));
+        const float fl = ((gm - 8.0f) + 4.0f) * 0.25f;
+        s_fix[0] = FixEntry{ob, pm < fl ? bt - ob * p.ntiles : -1, fl, pm == -__int_as_float(0x7f800000)};
+      }
+    }
+    __syncthreads();
+    const FixEntry fx = s_fix[0];
+    if (fx.tile == -2) break;
+    if (fx.tile >= 0) fix_tile(p, fx, warp, lane);
+    __syncthreads();
   }
 }
 
 // ---- per-clip mean / rstd for do_normalize (HF:...feature_extraction_whisper.py:168-187) ------------
 template <typename T>
 __global__ void __launch_bounds__(512) clip_stats_kernel(const void* pcm_, float scale, const int64_t* offsets,
-                                                         int n_samples, float2* stats) {
+                                                         const int64_t* lengths, int n_samples, float2* stats) {
   const int b = blockIdx.x;
   const int64_t off = offsets[b];
-  const int64_t avail = offsets[b + 1] - off;
+  const int64_t avail = lengths != nullptr ? lengths[b] : offsets[b + 1] - off;
   const int len = (int)(avail < (int64_t)n_samples ? avail : (int64_t)n_samples);
   const T* pcm = reinterpret_cast<const T*>(pcm_) + off;
   double s = 0.0, ss = 0.0;

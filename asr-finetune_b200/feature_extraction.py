@@ -225,8 +225,9 @@ class WhisperFeatureExtractor:
     # ---- the hot path -----------------------------------------------------------------------------------
     def logmel_device(self, pcm: torch.Tensor, offsets: torch.Tensor, batch: int, *, n_samples: Optional[int] = None,
                       pcm_scale: float = 1.0, do_normalize: bool = False, return_attention_mask: bool = False,
-                      out: Optional[torch.Tensor] = None):
-        """Device-resident entry: ragged `pcm` (float32 or int16 CUDA tensor) + int64 `offsets` (B+1, CUDA)
+                      out: Optional[torch.Tensor] = None, lengths: Optional[torch.Tensor] = None):
+        """Device-resident entry: ragged `pcm` (float32 or int16 CUDA tensor) + int64 `offsets` (CUDA; B+1 entries, or B
+        clip starts when `lengths` (B, int64, CUDA) is given — starts on 16-byte boundaries take the 128-bit load path)
         -> (input_features (B, n_mel, n_frames) fp32 CUDA, attention_mask (B, n_frames) int32 CUDA or None).
         Runs on the current torch stream; no host synchronisation."""
         dev = pcm.device
@@ -237,7 +238,10 @@ class WhisperFeatureExtractor:
             dt = _lib.WFE_PCM_I16
         else:
             raise TypeError(f"pcm must be float32 or int16, got {pcm.dtype}")
-        assert offsets.dtype == torch.int64 and offsets.is_cuda and offsets.numel() == batch + 1
+        assert offsets.dtype == torch.int64 and offsets.is_cuda
+        assert offsets.numel() == (batch + 1 if lengths is None else batch)
+        assert lengths is None or (lengths.dtype == torch.int64 and lengths.is_cuda and lengths.numel() == batch)
+        len_ptr = lengths.data_ptr() if lengths is not None else None
         if out is None:
             out = torch.empty((batch, h.n_mel, h.n_frames), dtype=torch.float32, device=dev)
         mask = torch.empty((batch, h.n_frames), dtype=torch.int32, device=dev) if return_attention_mask else None
@@ -246,10 +250,10 @@ class WhisperFeatureExtractor:
         stats_ptr = None
         if do_normalize:
             stats = torch.empty((batch, 2), dtype=torch.float32, device=dev)
-            _lib.check(h.lib.wfe_clip_stats(h.ptr, pcm.data_ptr(), dt, pcm_scale, offsets.data_ptr(), batch,
+            _lib.check(h.lib.wfe_clip_stats(h.ptr, pcm.data_ptr(), dt, pcm_scale, offsets.data_ptr(), len_ptr, batch,
                                             stats.data_ptr(), stream), "wfe_clip_stats")
             stats_ptr = stats.data_ptr()
-        _lib.check(h.lib.wfe_logmel(h.ptr, pcm.data_ptr(), dt, pcm_scale, offsets.data_ptr(), batch, stats_ptr,
+        _lib.check(h.lib.wfe_logmel(h.ptr, pcm.data_ptr(), dt, pcm_scale, offsets.data_ptr(), len_ptr, batch, stats_ptr,
                                     out.data_ptr(), mask.data_ptr() if mask is not None else None,
                                     scratch.data_ptr(), stream), "wfe_logmel")
         return out, mask
@@ -365,16 +369,20 @@ class WhisperFeatureExtractor:
         want_mask = bool(return_attention_mask if return_attention_mask is not None else self.return_attention_mask)
         norm = bool(do_normalize) if do_normalize is not None else bool(self.do_normalize)
         dt = torch.int16 if clips[0].dtype == torch.int16 else torch.float32
-        lens = [min(int(c.numel()), n_samples) for c in clips]
-        offs = np.zeros(len(clips) + 1, dtype=np.int64)
-        np.cumsum(lens, out=offs[1:])
+        B = len(clips)
+        lens = np.array([min(int(c.numel()), n_samples) for c in clips], dtype=np.int64)
+        meta = np.zeros(2 * B, dtype=np.int64)  # clip starts (16-byte aligned), then lengths: one H2D copy
+        meta[B:] = lens
+        if B > 1:
+            np.cumsum((lens[:-1] + 7) & ~7, out=meta[1:B])
+        total = int(meta[B - 1] + lens[-1])
         with torch.cuda.device(dev):
-            pcm = torch.empty(int(offs[-1]) + 8, dtype=dt, device=dev)
-            for c, o, n in zip(clips, offs[:-1], lens):
+            pcm = torch.empty(total + 8, dtype=dt, device=dev)
+            for c, o, n in zip(clips, meta[:B].tolist(), lens.tolist()):
                 pcm[o:o + n].copy_(c[:n].to(dt), non_blocking=True)
-            offsets = torch.from_numpy(offs).to(dev, non_blocking=True)
-            feats, mask = self.logmel_device(pcm, offsets, len(clips), n_samples=n_samples, do_normalize=norm,
-                                             return_attention_mask=want_mask)
+            d_meta = torch.from_numpy(meta).to(dev, non_blocking=True)
+            feats, mask = self.logmel_device(pcm, d_meta[:B], B, n_samples=n_samples, do_normalize=norm,
+                                             return_attention_mask=want_mask, lengths=d_meta[B:])
         keep = output_device is not None and str(output_device).startswith("cuda") or (output_device is None and clips[0].is_cuda)
         if not keep:
             feats = feats.cpu()

@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define WFE_ABI_VERSION 1
+#define WFE_ABI_VERSION 2
 
 typedef struct wfe_handle wfe_handle;
 
@@ -75,7 +75,8 @@ typedef struct wfe_config {
 
 /* mel_filters: HOST pointer, (n_fft/2+1, n_mel) row-major float32 — `fe.mel_filters.astype(float32)`,
  * the cast HF applies at use (HF:...feature_extraction_whisper.py:152).  The handle stores it in banded
- * (CSR-by-mel) form; any matrix with <= 4096 non-zeros is accepted. */
+ * (block-sparse, TF32) form for the tensor-pipe projection; it must be banded like every triangular mel bank
+ * (<= 64 non-zero 8-mel x 8-bin blocks; the Whisper banks have 32-33). */
 int wfe_create(const wfe_config* cfg, const float* mel_filters, wfe_handle** out);
 void wfe_destroy(wfe_handle* h);
 const char* wfe_last_error(void);
@@ -86,25 +87,31 @@ uint64_t wfe_launch_count(void);
 
 /* ---- log-mel features, device-resident input ---------------------------------------------------- */
 
-/* Bytes of device scratch wfe_logmel needs for `batch` clips (per-clip max/ticket + per-tile minima). */
+/* Bytes of device scratch wfe_logmel needs for `batch` clips (per-clip max + ticket, tile scheduler counter). */
 size_t wfe_logmel_scratch_bytes(const wfe_handle* h, int32_t batch);
 int32_t wfe_n_frames(const wfe_handle* h); /* n_samples / hop_length (3000) */
 
 /*
  * pcm        device, ragged concatenation of the batch's clips (dtype per pcm_dtype)
- * offsets    device, int64[batch+1]: clip b is pcm[offsets[b] .. offsets[b+1]); longer than n_samples is
- *            truncated, shorter is right-zero-padded (HF:feature_extraction_sequence_utils.py:265-278,327-332)
+ * offsets    device, int64: first sample of clip b in pcm.  With lengths == NULL it has batch+1 entries and clip b is
+ *            pcm[offsets[b] .. offsets[b+1]); with lengths != NULL it has batch entries and clip b is
+ *            pcm[offsets[b] .. offsets[b] + lengths[b]) (lets callers start every clip on a 16-byte boundary, which
+ *            is what enables the kernel's 128-bit load path; any alignment is still correct).  A clip longer than
+ *            n_samples is truncated, a shorter one is right-zero-padded
+ *            (HF:feature_extraction_sequence_utils.py:265-278,327-332)
+ * lengths    device, int64[batch] or NULL
  * norm_stats device, float2[batch] = (mean, 1/sqrt(var+1e-7)) from wfe_clip_stats, or NULL (do_normalize=False)
  * out        device, float32 (batch, n_mel, n_frames) C-contiguous  == BatchFeature["input_features"]
  * attn_mask  device, int32 (batch, n_frames) or NULL                == BatchFeature["attention_mask"]
  * scratch    device, wfe_logmel_scratch_bytes(h, batch) bytes; contents need not be initialised
  */
 int wfe_logmel(wfe_handle* h, const void* pcm, int32_t pcm_dtype, float pcm_scale, const int64_t* offsets,
-               int32_t batch, const float* norm_stats, float* out, int32_t* attn_mask, void* scratch, void* stream);
+               const int64_t* lengths, int32_t batch, const float* norm_stats, float* out, int32_t* attn_mask,
+               void* scratch, void* stream);
 
 /* Per-clip (mean, rstd) over the first min(len, n_samples) samples; stats: device float2[batch]. */
 int wfe_clip_stats(wfe_handle* h, const void* pcm, int32_t pcm_dtype, float pcm_scale, const int64_t* offsets,
-                   int32_t batch, float* stats, void* stream);
+                   const int64_t* lengths, int32_t batch, float* stats, void* stream);
 
 /* ---- collator, device-resident ------------------------------------------------------------------ */
 

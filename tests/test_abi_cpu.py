@@ -38,7 +38,7 @@ def test_header_symbols_all_exported(pkg):
     for s in syms:
         assert hasattr(lib, s), f"libwfe.so does not export {s} declared in include/wfe.h"
     assert sorted(pkg._lib.SYMBOLS) == syms, "asr_finetune_b200._lib.SYMBOLS is out of sync with include/wfe.h"
-    assert lib.wfe_abi_version() == 1
+    assert lib.wfe_abi_version() == 2
     assert lib.wfe_launch_count() == 0 or lib.wfe_launch_count() > 0  # callable without a device
 
 
@@ -77,7 +77,7 @@ def test_bad_config_is_rejected_before_touching_cuda(pkg):
     cfg = pkg._lib.WfeConfig(n_mel=128, n_fft=512, hop_length=160, n_samples=480000, sampling_rate=16000, device=0)
     assert lib.wfe_create(C.byref(cfg), filt.ctypes.data_as(C.c_void_p), C.byref(h)) == -2  # WFE_ERR_UNSUPPORTED
     assert lib.wfe_create(None, None, None) == -1
-    assert lib.wfe_logmel(None, None, 0, 1.0, None, 1, None, None, None, None, None) == -1
+    assert lib.wfe_logmel(None, None, 0, 1.0, None, None, 1, None, None, None, None, None) == -1
     assert lib.wfe_collate(None, None, None, 1, 1, 0, -100, None, None, None, 0, None, None) == -1
     assert lib.wfe_extract_host(None, None, None, 1, 0, 1.0, 0, None, None, None, None) == -1
 
