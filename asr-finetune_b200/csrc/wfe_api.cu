@@ -277,18 +277,21 @@ int wfe_create(const wfe_config* cfg, const float* mel_filters, wfe_handle** out
           hi = k > hi ? k : hi;
         }
     wfe::MelUnit u;
-    u.kstep0 = (int16_t)(btab.size() / 32);
-    u.nb = (int16_t)(8 * j);
+    u.kstep0 = (int32_t)(btab.size() / 32);
+    u.nb = 8 * j;
     if (hi < 0) {  // all-zero filters: one k-step of zeros keeps the epilogue (log10(1e-10)) uniform
       lo = 0;
       hi = 0;
     }
-    u.kb = (int16_t)lo;
-    u.ks = (int16_t)((hi - lo + 8) / 8);
+    u.kb = lo;
+    u.ks = (hi - lo + 8) / 8;
     for (int s = 0; s < u.ks; ++s)
       for (int lane = 0; lane < 32; ++lane) {
         const int g = lane >> 2, t = lane & 3, kb = lo + 8 * s;
-        btab.push_back(make_float2(tf32_rna(F(kb + t, 8 * j + g)), tf32_rna(F(kb + t + 4, 8 * j + g))));
+        // the kernel feeds the power values to the tensor core untouched, i.e. TRUNCATED to tf32 (relative error in
+        // (-2^-10, 0]); scaling the weights by 1 + 2^-11 centres that error at (-2^-11, 2^-11)
+        const float bias = 1.0f + 1.0f / 2048.0f;
+        btab.push_back(make_float2(tf32_rna(F(kb + t, 8 * j + g) * bias), tf32_rna(F(kb + t + 4, 8 * j + g) * bias)));
       }
     units.push_back(u);  // frames  0..15 of the tile
     units.push_back(u);  // frames 16..31

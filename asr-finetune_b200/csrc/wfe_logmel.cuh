@@ -58,11 +58,11 @@ template <>
 __device__ __forceinline__ float pcm_to_float<int16_t>(int16_t v, float scale) { return (float)v * scale; }
 
 // one mel-stage work unit: 8 mels x 16 frames, `ks` k-steps of 8 bins starting at bin `kb`
-struct MelUnit {
-  int16_t kstep0;  // first k-step (index into the B-fragment table)
-  int16_t ks;      // number of k-steps
-  int16_t kb;      // first bin
-  int16_t nb;      // first mel
+struct alignas(16) MelUnit {
+  int32_t kstep0;  // first k-step (index into the B-fragment table)
+  int32_t ks;      // number of k-steps
+  int32_t kb;      // first bin
+  int32_t nb;      // first mel
 };
 
 struct LogmelParams {
@@ -72,7 +72,7 @@ struct LogmelParams {
   const float2* norm;       // (mean, rstd) per clip or nullptr
   float* out;               // (B, n_mel, n_frames)
   int32_t* mask;            // (B, n_frames) or nullptr
-  uint32_t* clip_key;       // [B] running max of log10(mel) as ordered key (zero-initialised)
+  uint32_t* clip_key;       // [B] running max of the scaled feature y = (log10(mel)+4)/4 as ordered key (zero-init)
   uint32_t* clip_ticket;    // [B] finished-tile counter (zero-initialised)
   uint32_t* tile_counter;   // [1] dynamic tile scheduler (zero-initialised)
   const float4* s1_consts;  // [8][25] per-warp window/twiddle block
@@ -98,11 +98,6 @@ __device__ __forceinline__ void red_max_u32(uint32_t* p, uint32_t v) {
 __device__ __forceinline__ void red_release_add_u32(uint32_t* p, uint32_t v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ uint32_t f32_to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
 __device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -114,103 +109,135 @@ __device__ __forceinline__ float lg2_approx(float x) {
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
-// log10(max(v, 1e-10)); exactly -10 on the clamp so that silence is bit-identical to the reference (-1.5 after scaling)
-__device__ __forceinline__ float log10_clamped(float v) { return v > 1e-10f ? lg2_approx(v) * kLog10_2 : -10.0f; }
+// y = (log10(max(v, 1e-10)) + 4) / 4 in three instructions: MUFU.LG2, FFMA, FMNMX.  v <= 1e-10 (incl. lg2(0) = -inf)
+// lands on exactly -1.5 = (log10(1e-10) + 4) / 4, so silence is bit-identical to the reference.
+__device__ __forceinline__ float logmel_feature(float v) {
+  return fmaxf(fmaf(lg2_approx(v), 0.25f * kLog10_2, 1.0f), -1.5f);
+}
 
 struct FixEntry {
   int b, tile;       // tile < 0: nothing to do
-  float floor_y;     // ((g - 8) + 4) / 4
+  float floor_y;     // ((g - 8) + 4) / 4 = y_max - 2
   int silent;        // tile lies in the zero padding: store the constant instead of clamping
 };
 
 // apply the per-clip clamp to one of this CTA's own tiles (values come back from L2)
-__device__ __forceinline__ void fix_tile(const LogmelParams& p, const FixEntry& fx, int warp, int lane) {
+__device__ __forceinline__ void fix_tile(float* __restrict__ out, int n_mel, int n_frames, const FixEntry fx, int warp,
+                                         int lane) {
   const int t0 = fx.tile * kTileF;
-  if (t0 + lane >= p.n_frames) return;
-  float* q = p.out + ((size_t)fx.b * p.n_mel) * p.n_frames + t0 + lane;
+  if (t0 + lane >= n_frames) return;
+  float* q = out + ((size_t)fx.b * n_mel) * n_frames + t0 + lane;
   if (fx.silent) {
     const float y = fmaxf(-1.5f, fx.floor_y);  // (max(-10, g-8) + 4) / 4
-    for (int m = warp; m < p.n_mel; m += kWarps) q[(size_t)m * p.n_frames] = y;
+    for (int m = warp; m < n_mel; m += kWarps) q[(size_t)m * n_frames] = y;
   } else {
-    for (int m0 = warp; m0 < p.n_mel; m0 += 4 * kWarps) {
+    for (int m0 = warp; m0 < n_mel; m0 += 4 * kWarps) {
       float v[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int m = m0 + j * kWarps;
-        v[j] = m < p.n_mel ? __ldcg(q + (size_t)m * p.n_frames) : 3.0e38f;
+        v[j] = m < n_mel ? __ldcg(q + (size_t)m * n_frames) : 3.0e38f;
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int m = m0 + j * kWarps;
-        if (v[j] < fx.floor_y) q[(size_t)m * p.n_frames] = fx.floor_y;
+        if (v[j] < fx.floor_y) q[(size_t)m * n_frames] = fx.floor_y;
       }
     }
   }
 }
 
-__device__ __noinline__ void fix_tile_serial(const LogmelParams& p, const FixEntry fx) {
-  const int t0 = fx.tile * kTileF;
-  const int nv = min(kTileF, p.n_frames - t0);
-  float* q = p.out + ((size_t)fx.b * p.n_mel) * p.n_frames + t0;
-  const float ys = fmaxf(-1.5f, fx.floor_y);
-  for (int m = 0; m < p.n_mel; ++m)
-    for (int f = 0; f < nv; ++f) {
-      float* e = q + (size_t)m * p.n_frames + f;
-      if (fx.silent)
-        *e = ys;
-      else if (__ldcg(e) < fx.floor_y)
-        *e = fx.floor_y;
+// stage 0, synchronous: the tile's 5360 samples -> skewed smem.  kNorm selects the zero-mean/unit-variance variant.
+template <typename T, bool kNorm>
+__device__ __forceinline__ void stage_signal(float* __restrict__ sig, const T* __restrict__ pcm, int s_begin, int len,
+                                             int n_samples, float scale, float mean, float rstd, int tid) {
+  constexpr int kVec = 16 / (int)sizeof(T);  // samples per 128-bit load
+  const bool fast =
+      (s_begin >= 0) && (s_begin + kSigLen <= len) && ((reinterpret_cast<uintptr_t>(pcm + s_begin) & 15u) == 0);
+  if (fast) {
+    const uint4* src4 = reinterpret_cast<const uint4*>(pcm + s_begin);
+#pragma unroll 3
+    for (int v = tid; v < kSigLen / kVec; v += kThreads) {
+      const uint4 raw = __ldg(src4 + v);
+      const T* e = reinterpret_cast<const T*>(&raw);
+      const int i = v * kVec;
+      float* dst = sig + i + 2 * (i / kHop);  // 160 is a multiple of kVec: a vector never straddles a hop row
+#pragma unroll
+      for (int j = 0; j < kVec; j += 2) {
+        float2 o;
+        o.x = pcm_to_float<T>(e[j], scale);
+        o.y = pcm_to_float<T>(e[j + 1], scale);
+        if (kNorm) {
+          o.x = (o.x - mean) * rstd;
+          o.y = (o.y - mean) * rstd;
+        }
+        *reinterpret_cast<float2*>(dst + j) = o;
+      }
     }
+  } else {
+    for (int i = tid; i < kSigLen; i += kThreads) {
+      int s = s_begin + i;
+      if (s < 0) s = -s;
+      if (s >= n_samples) s = 2 * (n_samples - 1) - s;
+      float v = 0.f;
+      if (s >= 0 && s < len) {
+        v = pcm_to_float<T>(pcm[s], scale);
+        if (kNorm) v = (v - mean) * rstd;
+      }
+      sig[i + 2 * (i / kHop)] = v;
+    }
+  }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams p) {
   extern __shared__ __align__(16) float smem[];
-  float* const bufA = smem;                 // signal staging (stage 0-1), then power (stage 2-3)
+  float* const bufA = smem;  // signal staging (stage 0-1), then power (stage 2-3)
   float* const zbuf = smem + kBufA;
   float4* const s_cst = reinterpret_cast<float4*>(zbuf + kZSm);
   float2* const s_btab = reinterpret_cast<float2*>(s_cst + 8 * kS1ConstVec);
   __shared__ MelUnit s_units[kMaxUnits];
   __shared__ float s_red[2][kWarps];
-  __shared__ uint32_t s_next[2];
+  __shared__ int2 s_next[2];           // (clip, tile) of the next work item; clip < 0: no more work
   __shared__ FixEntry s_fix[2];
-  __shared__ int s_pend_bt[kRing];     // b * ntiles + tile  (tile id)
+  __shared__ int s_pend_bt[kRing];     // clip * ntiles + tile
   __shared__ float s_pend_min[kRing];  // tile minimum of y; -inf marks a silent (not yet written) tile
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float kNegInf = -__int_as_float(0x7f800000);
 
   // ---- one-time CTA set-up: constant blocks to smem, zero the k-padding rows of the power buffer ----
   for (int i = tid; i < 8 * kS1ConstVec; i += kThreads) s_cst[i] = p.s1_consts[i];
   for (int i = tid; i < p.n_ksteps * 32; i += kThreads) s_btab[i] = p.mel_btab[i];
   for (int i = tid; i < p.n_units; i += kThreads) s_units[i] = p.mel_units[i];
   for (int i = tid; i < (kPRows - kBins) * kPStride; i += kThreads) bufA[kBins * kPStride + i] = 0.f;
-  // frames >= 32 columns of the stride-40 rows are never read; no need to clear them
   if (tid == 0) {
-    s_next[0] = atomicAdd(p.tile_counter, 1u);
+    const uint32_t id = atomicAdd(p.tile_counter, 1u);
+    const int b0 = id < p.total_tiles ? (int)(id / (uint32_t)p.ntiles) : -1;
+    s_next[0] = make_int2(b0, (int)(id - (uint32_t)b0 * (uint32_t)p.ntiles));
     s_fix[0].tile = -1;
     s_fix[1].tile = -1;
   }
   __syncthreads();
 
-  // pending ring state lives in thread 0's registers
-  int ring_head = 0, ring_count = 0;
-  uint32_t cur = s_next[0];
+  int ring_head = 0, ring_count = 0;  // pending ring state (thread 0 only)
+  int2 cur = s_next[0];
   int parity = 0;
 
-  while (cur < p.total_tiles) {
-    const int b = (int)(cur / (uint32_t)p.ntiles), tile = (int)(cur - (uint32_t)b * (uint32_t)p.ntiles);
+  while (cur.x >= 0) {
+    const int b = cur.x, tile = cur.y;
     const int t0 = tile * kTileF;
-    const int64_t off = p.offsets[b];
-    const int64_t avail = (p.lengths != nullptr ? p.lengths[b] : p.offsets[b + 1] - off);
+    const int64_t off = __ldg(p.offsets + b);
+    const int64_t avail = (p.lengths != nullptr ? __ldg(p.lengths + b) : __ldg(p.offsets + b + 1) - off);
     const int len = (int)(avail < (int64_t)p.n_samples ? avail : (int64_t)p.n_samples);  // truncate to 30 s
     const int s_begin = t0 * kHop - kNFft / 2;  // unpadded sample index of sig[0]
     const int nvalid = min(kTileF, p.n_frames - t0);
 
     // thread 0: prefetch the next tile id and the tickets of the two oldest pending tiles (consumed much later)
-    uint32_t next_reg = 0, tk0 = 0, tk1 = 0;
+    uint32_t next_id = 0, tk0 = 0, tk1 = 0;
     int pb0 = -1, pb1 = -1;
     if (tid == 0) {
-      next_reg = atomicAdd(p.tile_counter, 1u);
+      next_id = atomicAdd(p.tile_counter, 1u);
       if (ring_count > 0) {
         pb0 = s_pend_bt[ring_head] / p.ntiles;
         tk0 = ld_acquire_u32(p.clip_ticket + pb0);
@@ -229,56 +256,30 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
     if (s_hi >= p.n_samples) lowest = min(lowest, 2 * (p.n_samples - 1) - s_hi);
     const bool silent = lowest >= len;  // every sample of every frame in the tile is zero padding
 
-    float tmax_l10 = -10.0f, tmin_y = 3.0e38f;
     if (!silent) {
       // ---- stage 0: PCM -> smem (skewed), with zero pad / reflect pad / optional normalisation ----
       const T* pcm = reinterpret_cast<const T*>(p.pcm) + off;
-      float mean = 0.f, rstd = 1.f;
       if (p.norm != nullptr) {
-        const float2 st = p.norm[b];
-        mean = st.x;
-        rstd = st.y;
-      }
-      constexpr int kVec = 16 / (int)sizeof(T);  // samples per 128-bit load
-      const bool fast = (s_begin >= 0) && (s_begin + kSigLen <= len) &&
-                        ((reinterpret_cast<uintptr_t>(pcm + s_begin) & 15u) == 0);
-      if (fast) {
-        const uint4* src4 = reinterpret_cast<const uint4*>(pcm + s_begin);
-#pragma unroll 2
-        for (int v = tid; v < kSigLen / kVec; v += kThreads) {
-          const uint4 raw = __ldg(src4 + v);
-          const T* e = reinterpret_cast<const T*>(&raw);
-          const int i = v * kVec;
-          float* dst = bufA + i + 2 * (i / kHop);  // 160 is a multiple of kVec: a vector never straddles a hop row
-#pragma unroll
-          for (int j = 0; j < kVec; j += 2) {
-            float2 o;
-            o.x = (pcm_to_float<T>(e[j], p.pcm_scale) - mean) * rstd;
-            o.y = (pcm_to_float<T>(e[j + 1], p.pcm_scale) - mean) * rstd;
-            *reinterpret_cast<float2*>(dst + j) = o;
-          }
-        }
+        const float2 st = __ldg(p.norm + b);
+        stage_signal<T, true>(bufA, pcm, s_begin, len, p.n_samples, p.pcm_scale, st.x, st.y, tid);
       } else {
-        for (int i = tid; i < kSigLen; i += kThreads) {
-          int s = s_begin + i;
-          if (s < 0) s = -s;
-          if (s >= p.n_samples) s = 2 * (p.n_samples - 1) - s;
-          float v = 0.f;
-          if (s >= 0 && s < len) v = (pcm_to_float<T>(pcm[s], p.pcm_scale) - mean) * rstd;
-          bufA[i + 2 * (i / kHop)] = v;
-        }
+        stage_signal<T, false>(bufA, pcm, s_begin, len, p.n_samples, p.pcm_scale, 0.f, 1.f, tid);
       }
     }
-    if (tid == 0) s_next[parity ^ 1] = next_reg;
+    if (tid == 0) {
+      const int nb = next_id < p.total_tiles ? (int)(next_id / (uint32_t)p.ntiles) : -1;
+      s_next[parity ^ 1] = make_int2(nb, (int)(next_id - (uint32_t)nb * (uint32_t)p.ntiles));
+    }
     __syncthreads();  // S1: signal staged; s_next and s_fix (from the previous tile's bookkeeping) published
 
     // ---- clamp fix-ups decided at the end of the previous tile (own tiles, L2-resident) ----
 #pragma unroll
     for (int f = 0; f < 2; ++f) {
       const FixEntry fx = s_fix[f];
-      if (fx.tile >= 0) fix_tile(p, fx, warp, lane);
+      if (fx.tile >= 0) fix_tile(p.out, p.n_mel, p.n_frames, fx, warp, lane);
     }
 
+    float tmax_y = -1.5f, tmin_y = 3.0e38f;
     if (!silent) {
       // ---- stage 1: warp w owns n1 = 2w, 2w+1 ----
       stage1_pair(bufA + kSigStride * lane, s_cst + warp * kS1ConstVec, 2 * warp, zbuf + lane);
@@ -292,45 +293,57 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
       // ---- stage 3: banded mel projection with mma.sync TF32, epilogue log10 / scale / store ----
       {
         const int g = lane >> 2, t = lane & 3;
-        float* const out_tile = p.out + ((size_t)b * p.n_mel) * p.n_frames + t0;
+        // this thread's output columns: frames mt+g, mt+g+8; rows: mels nb+2t, nb+2t+1
+        float* const out_lane = p.out + ((size_t)b * p.n_mel + 2 * t) * p.n_frames + t0 + g;
+        const bool full = nvalid == kTileF;
         for (int u = warp; u < p.n_units; u += kWarps) {
-          const MelUnit mu = s_units[u];
-          const int mt = u & 1 ? 16 : 0;  // units come in (frame-half 0, frame-half 1) pairs per mel tile
+          const int4 mu = *reinterpret_cast<const int4*>(&s_units[u]);  // kstep0, ks, kb, nb
+          const int mt = (u & 1) * 16;  // units come in (frames 0..15, frames 16..31) pairs per 8-mel tile
           float acc[4] = {0.f, 0.f, 0.f, 0.f};
-          const float* arow = bufA + (mu.kb + t) * kPStride + mt + g;
-          const float2* brow = s_btab + (int)mu.kstep0 * 32 + lane;
-          for (int s = 0; s < mu.ks; ++s) {
+          const float* arow = bufA + (mu.z + t) * kPStride + mt + g;
+          const float2* brow = s_btab + mu.x * 32 + lane;
+#pragma unroll 2
+          for (int s = 0; s < mu.y; ++s) {
+            // fp32 bit patterns go in as-is: the tensor core reads the top 19 bits (truncation); the filter weights
+            // carry a (1 + 2^-11) factor that centres the truncation error (see wfe_api.cu)
             uint32_t a[4];
-            a[0] = f32_to_tf32(arow[0]);
-            a[1] = f32_to_tf32(arow[8]);
-            a[2] = f32_to_tf32(arow[4 * kPStride]);
-            a[3] = f32_to_tf32(arow[4 * kPStride + 8]);
+            a[0] = __float_as_uint(arow[0]);
+            a[1] = __float_as_uint(arow[8]);
+            a[2] = __float_as_uint(arow[4 * kPStride]);
+            a[3] = __float_as_uint(arow[4 * kPStride + 8]);
             const float2 bw = *brow;
             mma_tf32_16x8x8(acc, a, __float_as_uint(bw.x), __float_as_uint(bw.y));
             arow += 8 * kPStride;
             brow += 32;
           }
           // c0: (frame mt+g, mel nb+2t)  c1: (mt+g, nb+2t+1)  c2: (mt+g+8, nb+2t)  c3: (mt+g+8, nb+2t+1)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int fr = mt + g + (c >> 1) * 8, m = mu.nb + 2 * t + (c & 1);
-            const float l10 = log10_clamped(acc[c]);
-            const float y = (l10 + 4.0f) * 0.25f;
-            if (fr < nvalid && m < p.n_mel) {
-              out_tile[(size_t)m * p.n_frames + fr] = y;
-              tmax_l10 = fmaxf(tmax_l10, l10);
-              tmin_y = fminf(tmin_y, y);
-            }
+          const float y0 = logmel_feature(acc[0]), y1 = logmel_feature(acc[1]);
+          const float y2 = logmel_feature(acc[2]), y3 = logmel_feature(acc[3]);
+          float* q = out_lane + (size_t)mu.w * p.n_frames + mt;
+          if (full && mu.w + 8 <= p.n_mel) {
+            q[0] = y0;
+            q[p.n_frames] = y1;
+            q[8] = y2;
+            q[p.n_frames + 8] = y3;
+            tmax_y = fmaxf(tmax_y, fmaxf(fmaxf(y0, y1), fmaxf(y2, y3)));
+            tmin_y = fminf(tmin_y, fminf(fminf(y0, y1), fminf(y2, y3)));
+          } else {
+            const bool f0 = mt + g < nvalid, f1 = mt + g + 8 < nvalid;
+            const bool m0 = mu.w + 2 * t < p.n_mel, m1 = mu.w + 2 * t + 1 < p.n_mel;
+            if (f0 && m0) { q[0] = y0; tmax_y = fmaxf(tmax_y, y0); tmin_y = fminf(tmin_y, y0); }
+            if (f0 && m1) { q[p.n_frames] = y1; tmax_y = fmaxf(tmax_y, y1); tmin_y = fminf(tmin_y, y1); }
+            if (f1 && m0) { q[8] = y2; tmax_y = fmaxf(tmax_y, y2); tmin_y = fminf(tmin_y, y2); }
+            if (f1 && m1) { q[p.n_frames + 8] = y3; tmax_y = fmaxf(tmax_y, y3); tmin_y = fminf(tmin_y, y3); }
           }
         }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
-        tmax_l10 = fmaxf(tmax_l10, __shfl_xor_sync(0xffffffffu, tmax_l10, o));
+        tmax_y = fmaxf(tmax_y, __shfl_xor_sync(0xffffffffu, tmax_y, o));
         tmin_y = fminf(tmin_y, __shfl_xor_sync(0xffffffffu, tmin_y, o));
       }
       if (lane == 0) {
-        s_red[0][warp] = tmax_l10;
+        s_red[0][warp] = tmax_y;
         s_red[1][warp] = tmin_y;
       }
     }
@@ -338,7 +351,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
 
     // ---- thread 0: publish the tile (clip max, ticket), remember it, decide the next fix-ups ----
     if (tid == 0) {
-      float mx = -10.0f, mn = -__int_as_float(0x7f800000);  // silent: max = log10(1e-10), min marker = -inf
+      float mx = -1.5f, mn = kNegInf;  // silent: max = (log10(1e-10)+4)/4, min marker = -inf
       if (!silent) {
         mx = s_red[0][0];
         mn = s_red[1][0];
@@ -353,22 +366,19 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
       // decide fix-ups for the (up to two) oldest pending tiles from the tickets read at the top of this tile
       int nfix = 0;
       if (pb0 >= 0 && tk0 == (uint32_t)p.ntiles) {
-        const float gmax = key2f(__ldcg(p.clip_key + pb0));
-        const float floor_y = ((gmax - 8.0f) + 4.0f) * 0.25f;
+        const float floor_y = key2f(__ldcg(p.clip_key + pb0)) - 2.0f;
         const int bt = s_pend_bt[ring_head];
         const float pm = s_pend_min[ring_head];
         ring_head = (ring_head + 1) & (kRing - 1);
         --ring_count;
-        if (pm < floor_y) s_fix[nfix++] = FixEntry{pb0, bt - pb0 * p.ntiles, floor_y, pm == -__int_as_float(0x7f800000)};
+        if (pm < floor_y) s_fix[nfix++] = FixEntry{pb0, bt - pb0 * p.ntiles, floor_y, pm == kNegInf};
         if (pb1 >= 0 && tk1 == (uint32_t)p.ntiles) {
-          const float gmax1 = key2f(__ldcg(p.clip_key + pb1));
-          const float floor1 = ((gmax1 - 8.0f) + 4.0f) * 0.25f;
+          const float floor1 = key2f(__ldcg(p.clip_key + pb1)) - 2.0f;
           const int bt1 = s_pend_bt[ring_head];
           const float pm1 = s_pend_min[ring_head];
           ring_head = (ring_head + 1) & (kRing - 1);
           --ring_count;
-          if (pm1 < floor1)
-            s_fix[nfix++] = FixEntry{pb1, bt1 - pb1 * p.ntiles, floor1, pm1 == -__int_as_float(0x7f800000)};
+          if (pm1 < floor1) s_fix[nfix++] = FixEntry{pb1, bt1 - pb1 * p.ntiles, floor1, pm1 == kNegInf};
         }
       }
       for (int f = nfix; f < 2; ++f) s_fix[f].tile = -1;
@@ -382,12 +392,15 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
         ring_head = (ring_head + 1) & (kRing - 1);
         --ring_count;
         while (ld_acquire_u32(p.clip_ticket + ob) != (uint32_t)p.ntiles) __nanosleep(200);
-        const float gm = key2f(__ldcg(p.clip_key + ob));
-        const float fl = ((gm - 8.0f) + 4.0f) * 0.25f;
-        if (pm < fl) fix_tile_serial(p, FixEntry{ob, bt - ob * p.ntiles, fl, pm == -__int_as_float(0x7f800000)});
+        const float fl = key2f(__ldcg(p.clip_key + ob)) - 2.0f;
+        if (pm < fl) {
+          const FixEntry fx{ob, bt - ob * p.ntiles, fl, pm == kNegInf};
+          for (int l = 0; l < 32; ++l)
+            for (int w = 0; w < kWarps; ++w) fix_tile(p.out, p.n_mel, p.n_frames, fx, w, l);
+        }
       }
       const int slot = (ring_head + ring_count) & (kRing - 1);
-      s_pend_bt[slot] = (int)cur;
+      s_pend_bt[slot] = b * p.ntiles + tile;
       s_pend_min[slot] = mn;
       ++ring_count;
     }
@@ -400,7 +413,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
 #pragma unroll
   for (int f = 0; f < 2; ++f) {
     const FixEntry fx = s_fix[f];
-    if (fx.tile >= 0) fix_tile(p, fx, warp, lane);
+    if (fx.tile >= 0) fix_tile(p.out, p.n_mel, p.n_frames, fx, warp, lane);
   }
   __syncthreads();
   for (;;) {
@@ -413,15 +426,14 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
         ring_head = (ring_head + 1) & (kRing - 1);
         --ring_count;
         while (ld_acquire_u32(p.clip_ticket + ob) != (uint32_t)p.ntiles) __nanosleep(100);
-        const float gm = key2f(__ldcg(p.clip_key + ob));
-        const float fl = ((gm - 8.0f) + 4.0f) * 0.25f;
-        s_fix[0] = FixEntry{ob, pm < fl ? bt - ob * p.ntiles : -1, fl, pm == -__int_as_float(0x7f800000)};
+        const float fl = key2f(__ldcg(p.clip_key + ob)) - 2.0f;
+        s_fix[0] = FixEntry{ob, pm < fl ? bt - ob * p.ntiles : -1, fl, pm == kNegInf};
       }
     }
     __syncthreads();
     const FixEntry fx = s_fix[0];
     if (fx.tile == -2) break;
-    if (fx.tile >= 0) fix_tile(p, fx, warp, lane);
+    if (fx.tile >= 0) fix_tile(p.out, p.n_mel, p.n_frames, fx, warp, lane);
     __syncthreads();
   }
 }
