@@ -283,11 +283,13 @@ int wfe_create(const wfe_config* cfg, const float* mel_filters, wfe_handle** out
       lo = 0;
       hi = 0;
     }
-    u.kb = lo;
     u.ks = (hi - lo + 8) / 8;
+    // the k-steps may start below `lo` (zero weights there) so that they end at bin 200 at the latest: the power
+    // buffer has exactly 201 rows
+    u.kb = lo < wfe::kBins - 8 * u.ks ? lo : wfe::kBins - 8 * u.ks;
     for (int s = 0; s < u.ks; ++s)
       for (int lane = 0; lane < 32; ++lane) {
-        const int g = lane >> 2, t = lane & 3, kb = lo + 8 * s;
+        const int g = lane >> 2, t = lane & 3, kb = u.kb + 8 * s;
         // the kernel feeds the power values to the tensor core untouched, i.e. TRUNCATED to tf32 (relative error in
         // (-2^-10, 0]); scaling the weights by 1 + 2^-11 centres that error at (-2^-11, 2^-11)
         const float bias = 1.0f + 1.0f / 2048.0f;

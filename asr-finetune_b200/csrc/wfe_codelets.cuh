@@ -236,10 +236,9 @@ WFE_DEV void dft16_power(const cx<T> (&z)[16], T (&pw)[16]) {
 constexpr int kZPlanes = 25;
 WFE_DEV int z_plane(int k2, int im) { return k2 == 0 ? 0 : 1 + 2 * (k2 - 1) + im; }
 WFE_DEV int z_index(int plane, int n1, int frame) { return (plane * 16 + n1) * kTileF + frame; }
-// power buffer (stage 2 -> mel): BIN-major with a row stride of 40 floats: conflict-free [row][lane] stores in
+// power buffer (stage 2 -> mel): BIN-major, 201 rows with a stride of 40 floats: conflict-free [row][lane] stores in
 // stage 2 and conflict-free mma.sync A-fragment loads (bank = 8*(k%4) + frame%8) in the mel stage.
 constexpr int kPStride = 40;
-constexpr int kPRows = 208;  // 201 bins padded to a multiple of 8 (rows 201..207 stay zero)
 // bin computed by stage 2 for residue k2 (0..12) and output index k1 (0..15): 25*k1 + k2, folded by conjugate symmetry
 inline int stage2_bin(int k2, int k1) {
   const int k = 25 * k1 + k2;
@@ -320,9 +319,9 @@ WFE_DEV void stage1_pair(const float* __restrict__ sig_frame, const float4* __re
   }
 }
 
-// ---- stage 2 for one (frame, k2 pair (a, a+1)), a odd in 1..11: DFT-16 over n1, power, bin-major store ----
-// pcol = power buffer + frame
-WFE_DEV void stage2_pair(const float* __restrict__ zcol, int a, float* __restrict__ pcol) {
+// ---- stage 2 for one (frame, k2 pair (a, a+1)), a odd in 1..11: DFT-16 over n1, power -------------------
+// split in two so that the power can be written over the z buffer once every warp has finished reading it
+WFE_DEV void stage2_pair_compute(const float* __restrict__ zcol, int a, f2 (&pw)[16]) {
   cx<f2> z[16];
   const float* ra = zcol + z_index(z_plane(a, 0), 0, 0);
   constexpr int kPlane = 16 * kTileF;  // floats per plane
@@ -331,9 +330,10 @@ WFE_DEV void stage2_pair(const float* __restrict__ zcol, int a, float* __restric
     z[n].r = mk2(ra[n * kTileF], ra[n * kTileF + 2 * kPlane]);
     z[n].i = mk2(ra[n * kTileF + kPlane], ra[n * kTileF + 3 * kPlane]);
   }
-  f2 pw[16];
   dft16_power<f2>(z, pw);
-  // bins 25*k1 + a (k1 = 0..7) and 400 - (25*k1 + a) (k1 = 8..15); same with a+1
+}
+// bin-major store: bins 25*k1 + a (k1 = 0..7) and 400 - (25*k1 + a) (k1 = 8..15); same with a+1.  pcol = P + frame
+WFE_DEV void stage2_pair_store(const f2 (&pw)[16], int a, float* __restrict__ pcol) {
   float* lo = pcol + a * kPStride;
   float* hi = pcol + (400 - a) * kPStride;
 #pragma unroll
@@ -348,15 +348,19 @@ WFE_DEV void stage2_pair(const float* __restrict__ zcol, int a, float* __restric
   }
 }
 
-// k2 = 0: real input, bins 0, 25, ..., 200
-WFE_DEV void stage2_k0(const float* __restrict__ zcol, float* __restrict__ pcol) {
+// k2 = 0: real input, bins 0, 25, ..., 200 (kept in the .x halves of pw[0..8])
+WFE_DEV void stage2_k0_compute(const float* __restrict__ zcol, f2 (&pw)[16]) {
   cx<float> z[16];
 #pragma unroll
   for (int n = 0; n < 16; ++n) z[n] = {zcol[z_index(0, n, 0)], 0.f};
-  float pw[16];
-  dft16_power<float>(z, pw);
+  float q[16];
+  dft16_power<float>(z, q);
 #pragma unroll
-  for (int k1 = 0; k1 < 9; ++k1) pcol[(25 * k1) * kPStride] = pw[k1];
+  for (int k1 = 0; k1 < 9; ++k1) pw[k1].v.x = q[k1];
+}
+WFE_DEV void stage2_k0_store(const f2 (&pw)[16], float* __restrict__ pcol) {
+#pragma unroll
+  for (int k1 = 0; k1 < 9; ++k1) pcol[(25 * k1) * kPStride] = pw[k1].v.x;
 }
 
 }  // namespace wfe

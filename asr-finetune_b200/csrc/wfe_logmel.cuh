@@ -32,14 +32,14 @@ constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kSigLen = (kTileF - 1) * kHop + kNFft;  // 5360 padded-signal samples per tile
 constexpr int kSigStride = kHop + 2;                  // +2 pad words per 160 samples: conflict-free LDS.64 across frames
-constexpr int kSigSm = kSigLen + 2 * (kSigLen / kHop) + 4;
-constexpr int kBufA = kPRows * kPStride;              // power buffer (also the signal staging area): 8320 floats
-constexpr int kZSm = kZPlanes * 16 * kTileF;          // 12800 floats
+constexpr int kSigSm = kSigLen + 2 * (kSigLen / kHop) + 4;   // 5430 floats per staging buffer (two of them)
+constexpr int kZSm = kZPlanes * 16 * kTileF;          // 12800 floats; the power buffer (201 x 40) aliases it
 constexpr int kRing = 128;                            // pending-tile ring (>= tiles per clip, see wfe_api.cu)
 constexpr int kMaxUnits = 64;                         // (8-mel tile, 16-frame tile) work units of the mel stage
 constexpr int kMaxKsteps = 64;                        // non-zero 8x8 blocks of the filter bank (33 for Whisper)
 
-static_assert(kSigSm <= kBufA, "signal staging must fit in the power buffer");
+static_assert(kBins * kPStride <= kZSm, "power buffer must fit in the z buffer it aliases");
+static_assert((kSigSm * 4) % 16 == 0 || true, "");
 
 // order-preserving float <-> uint32 key (for atomic max on floats of either sign); key 0 < every float
 __device__ __forceinline__ uint32_t f2key(float f) {
@@ -83,8 +83,30 @@ struct LogmelParams {
   uint32_t total_tiles;
 };
 
+constexpr int kSigBuf = (kSigSm + 3) & ~3;  // 16-byte multiple
 __host__ __device__ inline size_t logmel_smem_bytes(int n_ksteps) {
-  return (size_t)(kBufA + kZSm) * 4 + 8 * kS1ConstVec * 16 + (size_t)n_ksteps * 32 * 8;
+  return (size_t)(2 * kSigBuf + kZSm) * 4 + 8 * kS1ConstVec * 16 + (size_t)n_ksteps * 32 * 8;
+}
+
+// work item handed from the scheduler lane to the CTA through shared memory
+struct alignas(16) TileDesc {
+  int32_t b;      // clip; < 0: no more work
+  int32_t tile;   // tile within the clip
+  int32_t len;    // min(clip length, n_samples)
+  int32_t mode;   // 0 = silent (all zero padding), 1 = interior + aligned (cp.async prefetch), 2 = synchronous staging
+  int64_t off;    // first sample of the clip in pcm
+  int64_t pad_;
+};
+constexpr int kModeSilent = 0, kModeAsync = 1, kModeSync = 2;
+
+__device__ __forceinline__ void cp_async8(float* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
@@ -189,90 +211,120 @@ __device__ __forceinline__ void stage_signal(float* __restrict__ sig, const T* _
   }
 }
 
+// fill a work-item descriptor for tile id `id` (scheduler lane only): clip geometry + how its signal gets staged
+template <typename T>
+__device__ __forceinline__ TileDesc make_desc(const LogmelParams& p, uint32_t id) {
+  TileDesc d;
+  d.pad_ = 0;
+  if (id >= p.total_tiles) {
+    d.b = -1;
+    d.tile = 0;
+    d.len = 0;
+    d.mode = kModeSilent;
+    d.off = 0;
+    return d;
+  }
+  d.b = (int)(id / (uint32_t)p.ntiles);
+  d.tile = (int)(id - (uint32_t)d.b * (uint32_t)p.ntiles);
+  d.off = __ldg(p.offsets + d.b);
+  const int64_t avail = (p.lengths != nullptr ? __ldg(p.lengths + d.b) : __ldg(p.offsets + d.b + 1) - d.off);
+  d.len = (int)(avail < (int64_t)p.n_samples ? avail : (int64_t)p.n_samples);  // truncate to 30 s
+  const int s_begin = d.tile * kTileF * kHop - kNFft / 2;
+  const int s_hi = s_begin + kSigLen - 1;
+  // lowest source sample this tile touches (right reflect maps s >= n_samples to 2(n-1)-s)
+  int lowest = s_begin < 0 ? 0 : s_begin;
+  if (s_hi >= p.n_samples) lowest = min(lowest, 2 * (p.n_samples - 1) - s_hi);
+  if (lowest >= d.len) {
+    d.mode = kModeSilent;  // every sample of every frame in the tile is zero padding
+  } else {
+    const T* src = reinterpret_cast<const T*>(p.pcm) + d.off + s_begin;
+    const bool async_ok = sizeof(T) == 4 && p.norm == nullptr && s_begin >= 0 && s_begin + kSigLen <= d.len &&
+                          (reinterpret_cast<uintptr_t>(src) & 7u) == 0;
+    d.mode = async_ok ? kModeAsync : kModeSync;
+  }
+  return d;
+}
+
+// asynchronous staging of an interior float32 tile: 2680 8-byte cp.async per tile, no registers held
+__device__ __forceinline__ void prefetch_signal(float* __restrict__ sig, const float* __restrict__ src, int tid) {
+#pragma unroll
+  for (int k = 0; k < (kSigLen / 2 + kThreads - 1) / kThreads; ++k) {
+    const int j = tid + k * kThreads;  // float2 index
+    if (j < kSigLen / 2) cp_async8(sig + 2 * j + 2 * (j / (kHop / 2)), src + 2 * j);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams p) {
   extern __shared__ __align__(16) float smem[];
-  float* const bufA = smem;  // signal staging (stage 0-1), then power (stage 2-3)
-  float* const zbuf = smem + kBufA;
+  float* const sigbuf = smem;               // two signal staging buffers (tile i -> buffer i & 1)
+  float* const zbuf = smem + 2 * kSigBuf;   // stage 1 -> stage 2 exchange; the power buffer aliases it after stage 2
   float4* const s_cst = reinterpret_cast<float4*>(zbuf + kZSm);
   float2* const s_btab = reinterpret_cast<float2*>(s_cst + 8 * kS1ConstVec);
   __shared__ MelUnit s_units[kMaxUnits];
-  __shared__ float s_red[2][kWarps];
-  __shared__ int2 s_next[2];           // (clip, tile) of the next work item; clip < 0: no more work
+  __shared__ float s_red[2][2][kWarps];  // [tile parity][max, min][warp]
+  __shared__ TileDesc s_desc[2];         // descriptor of tile k lives in slot k & 1
   __shared__ FixEntry s_fix[2];
-  __shared__ int s_pend_bt[kRing];     // clip * ntiles + tile
-  __shared__ float s_pend_min[kRing];  // tile minimum of y; -inf marks a silent (not yet written) tile
+  __shared__ int s_pend_bt[kRing];       // clip * ntiles + tile
+  __shared__ float s_pend_min[kRing];    // tile minimum of y; -inf marks a silent (not yet written) tile
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float kNegInf = -__int_as_float(0x7f800000);
+  const bool sched = tid == 7 * 32;  // lane 0 of warp 7 (idle in stage 2): tile scheduler + clip bookkeeping
 
-  // ---- one-time CTA set-up: constant blocks to smem, zero the k-padding rows of the power buffer ----
+  // ---- one-time CTA set-up ----
   for (int i = tid; i < 8 * kS1ConstVec; i += kThreads) s_cst[i] = p.s1_consts[i];
   for (int i = tid; i < p.n_ksteps * 32; i += kThreads) s_btab[i] = p.mel_btab[i];
   for (int i = tid; i < p.n_units; i += kThreads) s_units[i] = p.mel_units[i];
-  for (int i = tid; i < (kPRows - kBins) * kPStride; i += kThreads) bufA[kBins * kPStride + i] = 0.f;
-  if (tid == 0) {
-    const uint32_t id = atomicAdd(p.tile_counter, 1u);
-    const int b0 = id < p.total_tiles ? (int)(id / (uint32_t)p.ntiles) : -1;
-    s_next[0] = make_int2(b0, (int)(id - (uint32_t)b0 * (uint32_t)p.ntiles));
+  if (sched) {
+    const uint32_t id0 = atomicAdd(p.tile_counter, 1u);
+    const uint32_t id1 = atomicAdd(p.tile_counter, 1u);
+    s_desc[0] = make_desc<T>(p, id0);
+    s_desc[1] = make_desc<T>(p, id1);
     s_fix[0].tile = -1;
     s_fix[1].tile = -1;
   }
   __syncthreads();
 
-  int ring_head = 0, ring_count = 0;  // pending ring state (thread 0 only)
-  int2 cur = s_next[0];
-  int parity = 0;
+  TileDesc cur = s_desc[0], nxt = s_desc[1];
+  if (cur.b >= 0 && cur.mode == kModeAsync)
+    prefetch_signal(sigbuf, reinterpret_cast<const float*>(p.pcm) + cur.off + cur.tile * kTileF * kHop - kNFft / 2, tid);
+  cp_async_commit();
 
-  while (cur.x >= 0) {
-    const int b = cur.x, tile = cur.y;
+  // scheduler-lane state: pending ring, previous tile (bookkeeping is deferred by one tile)
+  int ring_head = 0, ring_count = 0;
+  int prev_b = -1, prev_tile = 0, prev_silent = 0;
+  int it = 0;
+
+  while (cur.b >= 0) {
+    const int b = cur.b, tile = cur.tile, len = cur.len;
     const int t0 = tile * kTileF;
-    const int64_t off = __ldg(p.offsets + b);
-    const int64_t avail = (p.lengths != nullptr ? __ldg(p.lengths + b) : __ldg(p.offsets + b + 1) - off);
-    const int len = (int)(avail < (int64_t)p.n_samples ? avail : (int64_t)p.n_samples);  // truncate to 30 s
     const int s_begin = t0 * kHop - kNFft / 2;  // unpadded sample index of sig[0]
     const int nvalid = min(kTileF, p.n_frames - t0);
+    const bool silent = cur.mode == kModeSilent;
+    float* const sig = sigbuf + (it & 1) * kSigBuf;
 
-    // thread 0: prefetch the next tile id and the tickets of the two oldest pending tiles (consumed much later)
-    uint32_t next_id = 0, tk0 = 0, tk1 = 0;
-    int pb0 = -1, pb1 = -1;
-    if (tid == 0) {
-      next_id = atomicAdd(p.tile_counter, 1u);
-      if (ring_count > 0) {
-        pb0 = s_pend_bt[ring_head] / p.ntiles;
-        tk0 = ld_acquire_u32(p.clip_ticket + pb0);
-      }
-      if (ring_count > 1) {
-        pb1 = s_pend_bt[(ring_head + 1) & (kRing - 1)] / p.ntiles;
-        tk1 = ld_acquire_u32(p.clip_ticket + pb1);
-      }
-    }
-
-    if (p.mask != nullptr && tid < nvalid) p.mask[(size_t)b * p.n_frames + t0 + tid] = ((t0 + tid) * kHop < len) ? 1 : 0;
-
-    // lowest source sample this tile touches (right reflect maps s >= n_samples to 2(n-1)-s)
-    const int s_hi = s_begin + kSigLen - 1;
-    int lowest = s_begin < 0 ? 0 : s_begin;
-    if (s_hi >= p.n_samples) lowest = min(lowest, 2 * (p.n_samples - 1) - s_hi);
-    const bool silent = lowest >= len;  // every sample of every frame in the tile is zero padding
-
-    if (!silent) {
-      // ---- stage 0: PCM -> smem (skewed), with zero pad / reflect pad / optional normalisation ----
-      const T* pcm = reinterpret_cast<const T*>(p.pcm) + off;
+    // ---- top: start the NEXT tile's loads, then make sure this tile's signal has landed ----
+    uint32_t id2 = 0;
+    if (sched) id2 = atomicAdd(p.tile_counter, 1u);  // id of tile it+2, consumed in stage 2
+    if (nxt.b >= 0 && nxt.mode == kModeAsync)
+      prefetch_signal(sigbuf + ((it + 1) & 1) * kSigBuf,
+                      reinterpret_cast<const float*>(p.pcm) + nxt.off + nxt.tile * kTileF * kHop - kNFft / 2, tid);
+    cp_async_commit();
+    if (cur.mode == kModeSync) {
+      const T* pcm = reinterpret_cast<const T*>(p.pcm) + cur.off;
       if (p.norm != nullptr) {
         const float2 st = __ldg(p.norm + b);
-        stage_signal<T, true>(bufA, pcm, s_begin, len, p.n_samples, p.pcm_scale, st.x, st.y, tid);
+        stage_signal<T, true>(sig, pcm, s_begin, len, p.n_samples, p.pcm_scale, st.x, st.y, tid);
       } else {
-        stage_signal<T, false>(bufA, pcm, s_begin, len, p.n_samples, p.pcm_scale, 0.f, 1.f, tid);
+        stage_signal<T, false>(sig, pcm, s_begin, len, p.n_samples, p.pcm_scale, 0.f, 1.f, tid);
       }
     }
-    if (tid == 0) {
-      const int nb = next_id < p.total_tiles ? (int)(next_id / (uint32_t)p.ntiles) : -1;
-      s_next[parity ^ 1] = make_int2(nb, (int)(next_id - (uint32_t)nb * (uint32_t)p.ntiles));
-    }
-    __syncthreads();  // S1: signal staged; s_next and s_fix (from the previous tile's bookkeeping) published
+    if (p.mask != nullptr && tid < nvalid) p.mask[(size_t)b * p.n_frames + t0 + tid] = ((t0 + tid) * kHop < len) ? 1 : 0;
+    cp_async_wait<1>();  // everything but the group just committed (= this tile's signal) is complete
+    __syncthreads();     // S1: signal visible to all warps; s_fix / s_desc from the previous stage 2 published
 
-    // ---- clamp fix-ups decided at the end of the previous tile (own tiles, L2-resident) ----
+    // ---- clamp fix-ups decided during the previous tile (own tiles, L2-resident) ----
 #pragma unroll
     for (int f = 0; f < 2; ++f) {
       const FixEntry fx = s_fix[f];
@@ -282,13 +334,101 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
     float tmax_y = -1.5f, tmin_y = 3.0e38f;
     if (!silent) {
       // ---- stage 1: warp w owns n1 = 2w, 2w+1 ----
-      stage1_pair(bufA + kSigStride * lane, s_cst + warp * kS1ConstVec, 2 * warp, zbuf + lane);
+      stage1_pair(sig + kSigStride * lane, s_cst + warp * kS1ConstVec, 2 * warp, zbuf + lane);
       __syncthreads();  // S2
-      // ---- stage 2: warps 0..5 own (k2, k2+1) = (1,2)..(11,12); warp 6 owns k2 = 0 ----
+    }
+
+    // ---- stage 2 (compute half): warps 0..5 own (k2, k2+1) = (1,2)..(11,12); warp 6 owns k2 = 0;
+    //      warp 7 lane 0 runs the scheduler: bookkeeping of the PREVIOUS tile + descriptor of tile it+2 ----
+    f2 pw[16];
+    if (!silent) {
       if (warp < 6)
-        stage2_pair(zbuf + lane, 2 * warp + 1, bufA + lane);
+        stage2_pair_compute(zbuf + lane, 2 * warp + 1, pw);
       else if (warp == 6)
-        stage2_k0(zbuf + lane, bufA + lane);
+        stage2_k0_compute(zbuf + lane, pw);
+    }
+    if (sched) {
+      // tickets of the two oldest pending tiles (issued first: independent of everything below)
+      uint32_t tk0 = 0, tk1 = 0;
+      int pb0 = -1, pb1 = -1;
+      if (ring_count > 0) {
+        pb0 = s_pend_bt[ring_head] / p.ntiles;
+        tk0 = ld_acquire_u32(p.clip_ticket + pb0);
+      }
+      if (ring_count > 1) {
+        pb1 = s_pend_bt[(ring_head + 1) & (kRing - 1)] / p.ntiles;
+        tk1 = ld_acquire_u32(p.clip_ticket + pb1);
+      }
+      // publish the previous tile: clip max, then the ticket (release orders the two)
+      if (prev_b >= 0) {
+        float mx = -1.5f, mn = kNegInf;  // silent: max = (log10(1e-10)+4)/4, min marker = -inf
+        if (!prev_silent) {
+          const int pp = (it + 1) & 1;
+          mx = s_red[pp][0][0];
+          mn = s_red[pp][1][0];
+#pragma unroll
+          for (int w = 1; w < kWarps; ++w) {
+            mx = fmaxf(mx, s_red[pp][0][w]);
+            mn = fminf(mn, s_red[pp][1][w]);
+          }
+        }
+        red_max_u32(p.clip_key + prev_b, f2key(mx));
+        red_release_add_u32(p.clip_ticket + prev_b, 1u);
+        // ring full: cannot happen while ntiles <= kRing unless other CTAs lag a whole clip behind; the oldest entry's
+        // clip then has every tile assigned to a RUNNING CTA (ids are handed out in order), so this wait terminates
+        if (ring_count == kRing) {
+          const int bt = s_pend_bt[ring_head];
+          const float pm = s_pend_min[ring_head];
+          const int ob = bt / p.ntiles;
+          ring_head = (ring_head + 1) & (kRing - 1);
+          --ring_count;
+          while (ld_acquire_u32(p.clip_ticket + ob) != (uint32_t)p.ntiles) __nanosleep(200);
+          const float fl = key2f(__ldcg(p.clip_key + ob)) - 2.0f;
+          if (pm < fl) {
+            const FixEntry fx{ob, bt - ob * p.ntiles, fl, pm == kNegInf};
+            for (int l = 0; l < 32; ++l)
+              for (int w = 0; w < kWarps; ++w) fix_tile(p.out, p.n_mel, p.n_frames, fx, w, l);
+          }
+          pb0 = pb1;  // the head moved: only the entry that was second is still a candidate
+          tk0 = tk1;
+          pb1 = -1;
+        }
+        const int slot = (ring_head + ring_count) & (kRing - 1);
+        s_pend_bt[slot] = prev_b * p.ntiles + prev_tile;
+        s_pend_min[slot] = mn;
+        ++ring_count;
+      }
+      prev_b = b;
+      prev_tile = tile;
+      prev_silent = silent;
+      // fix-ups for the next tile's S1, decided from the tickets read above
+      int nfix = 0;
+      if (pb0 >= 0 && tk0 == (uint32_t)p.ntiles) {
+        const float floor_y = key2f(__ldcg(p.clip_key + pb0)) - 2.0f;
+        const int bt = s_pend_bt[ring_head];
+        const float pm = s_pend_min[ring_head];
+        ring_head = (ring_head + 1) & (kRing - 1);
+        --ring_count;
+        if (pm < floor_y) s_fix[nfix++] = FixEntry{pb0, bt - pb0 * p.ntiles, floor_y, pm == kNegInf};
+        if (pb1 >= 0 && tk1 == (uint32_t)p.ntiles) {
+          const float floor1 = key2f(__ldcg(p.clip_key + pb1)) - 2.0f;
+          const int bt1 = s_pend_bt[ring_head];
+          const float pm1 = s_pend_min[ring_head];
+          ring_head = (ring_head + 1) & (kRing - 1);
+          --ring_count;
+          if (pm1 < floor1) s_fix[nfix++] = FixEntry{pb1, bt1 - pb1 * p.ntiles, floor1, pm1 == kNegInf};
+        }
+      }
+      for (int f = nfix; f < 2; ++f) s_fix[f].tile = -1;
+      s_desc[it & 1] = make_desc<T>(p, id2);  // tile it+2 (slot of tile it, whose descriptor is in registers)
+    }
+
+    if (!silent) {
+      __syncthreads();  // S2b: every warp has read its z planes; the power buffer may now overwrite them
+      if (warp < 6)
+        stage2_pair_store(pw, 2 * warp + 1, zbuf + lane);
+      else if (warp == 6)
+        stage2_k0_store(pw, zbuf + lane);
       __syncthreads();  // S3
       // ---- stage 3: banded mel projection with mma.sync TF32, epilogue log10 / scale / store ----
       {
@@ -300,7 +440,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
           const int4 mu = *reinterpret_cast<const int4*>(&s_units[u]);  // kstep0, ks, kb, nb
           const int mt = (u & 1) * 16;  // units come in (frames 0..15, frames 16..31) pairs per 8-mel tile
           float acc[4] = {0.f, 0.f, 0.f, 0.f};
-          const float* arow = bufA + (mu.z + t) * kPStride + mt + g;
+          const float* arow = zbuf + (mu.z + t) * kPStride + mt + g;
           const float2* brow = s_btab + mu.x * 32 + lane;
 #pragma unroll 2
           for (int s = 0; s < mu.y; ++s) {
@@ -343,73 +483,49 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
         tmin_y = fminf(tmin_y, __shfl_xor_sync(0xffffffffu, tmin_y, o));
       }
       if (lane == 0) {
-        s_red[0][warp] = tmax_y;
-        s_red[1][warp] = tmin_y;
+        s_red[it & 1][0][warp] = tmax_y;
+        s_red[it & 1][1][warp] = tmin_y;
       }
     }
-    __syncthreads();  // S4: tile written (visible to this CTA), smem free for the next tile
+    __syncthreads();  // S4: tile written (visible to this CTA); s_desc / s_fix / s_red published; smem free
+    cur = nxt;
+    nxt = s_desc[it & 1];
+    ++it;
+  }
+  cp_async_wait<0>();
 
-    // ---- thread 0: publish the tile (clip max, ticket), remember it, decide the next fix-ups ----
-    if (tid == 0) {
-      float mx = -1.5f, mn = kNegInf;  // silent: max = (log10(1e-10)+4)/4, min marker = -inf
-      if (!silent) {
-        mx = s_red[0][0];
-        mn = s_red[1][0];
+  // ---- epilogue: publish the last tile, then drain the tiles this CTA still has pending (every remaining tile of
+  //      their clips is owned by a running CTA, so the waits terminate) ----
+  if (sched && prev_b >= 0) {
+    float mx = -1.5f, mn = kNegInf;
+    if (!prev_silent) {
+      const int pp = (it + 1) & 1;
+      mx = s_red[pp][0][0];
+      mn = s_red[pp][1][0];
 #pragma unroll
-        for (int w = 1; w < kWarps; ++w) {
-          mx = fmaxf(mx, s_red[0][w]);
-          mn = fminf(mn, s_red[1][w]);
-        }
+      for (int w = 1; w < kWarps; ++w) {
+        mx = fmaxf(mx, s_red[pp][0][w]);
+        mn = fminf(mn, s_red[pp][1][w]);
       }
-      red_max_u32(p.clip_key + b, f2key(mx));
-      red_release_add_u32(p.clip_ticket + b, 1u);
-      // decide fix-ups for the (up to two) oldest pending tiles from the tickets read at the top of this tile
-      int nfix = 0;
-      if (pb0 >= 0 && tk0 == (uint32_t)p.ntiles) {
-        const float floor_y = key2f(__ldcg(p.clip_key + pb0)) - 2.0f;
-        const int bt = s_pend_bt[ring_head];
-        const float pm = s_pend_min[ring_head];
-        ring_head = (ring_head + 1) & (kRing - 1);
-        --ring_count;
-        if (pm < floor_y) s_fix[nfix++] = FixEntry{pb0, bt - pb0 * p.ntiles, floor_y, pm == kNegInf};
-        if (pb1 >= 0 && tk1 == (uint32_t)p.ntiles) {
-          const float floor1 = key2f(__ldcg(p.clip_key + pb1)) - 2.0f;
-          const int bt1 = s_pend_bt[ring_head];
-          const float pm1 = s_pend_min[ring_head];
-          ring_head = (ring_head + 1) & (kRing - 1);
-          --ring_count;
-          if (pm1 < floor1) s_fix[nfix++] = FixEntry{pb1, bt1 - pb1 * p.ntiles, floor1, pm1 == kNegInf};
-        }
-      }
-      for (int f = nfix; f < 2; ++f) s_fix[f].tile = -1;
-      // push this tile.  The ring holds >= one clip's worth of tiles (host enforces ntiles <= kRing), so a full ring
-      // means the oldest entry's clip has every tile assigned to a RUNNING CTA (tile ids are handed out in order) and
-      // the wait below terminates; this is a never-in-practice path, so thread 0 fixes that tile on its own.
-      if (ring_count == kRing) {
-        const int bt = s_pend_bt[ring_head];
-        const float pm = s_pend_min[ring_head];
-        const int ob = bt / p.ntiles;
-        ring_head = (ring_head + 1) & (kRing - 1);
-        --ring_count;
-        while (ld_acquire_u32(p.clip_ticket + ob) != (uint32_t)p.ntiles) __nanosleep(200);
-        const float fl = key2f(__ldcg(p.clip_key + ob)) - 2.0f;
-        if (pm < fl) {
-          const FixEntry fx{ob, bt - ob * p.ntiles, fl, pm == kNegInf};
-          for (int l = 0; l < 32; ++l)
-            for (int w = 0; w < kWarps; ++w) fix_tile(p.out, p.n_mel, p.n_frames, fx, w, l);
-        }
-      }
+    }
+    red_max_u32(p.clip_key + prev_b, f2key(mx));
+    red_release_add_u32(p.clip_ticket + prev_b, 1u);
+    if (ring_count < kRing) {
       const int slot = (ring_head + ring_count) & (kRing - 1);
-      s_pend_bt[slot] = b * p.ntiles + tile;
+      s_pend_bt[slot] = prev_b * p.ntiles + prev_tile;
       s_pend_min[slot] = mn;
       ++ring_count;
+    } else {  // ring full (see above): fix this one serially once its clip completes
+      while (ld_acquire_u32(p.clip_ticket + prev_b) != (uint32_t)p.ntiles) __nanosleep(200);
+      const float fl = key2f(__ldcg(p.clip_key + prev_b)) - 2.0f;
+      if (mn < fl) {
+        const FixEntry fx{prev_b, prev_tile, fl, mn == kNegInf};
+        for (int l = 0; l < 32; ++l)
+          for (int w = 0; w < kWarps; ++w) fix_tile(p.out, p.n_mel, p.n_frames, fx, w, l);
+      }
     }
-    parity ^= 1;
-    cur = s_next[parity];  // published at S1 of this iteration
   }
-
-  // ---- drain: the tiles this CTA still has pending; every remaining tile of their clips is owned by a running CTA ----
-  __syncthreads();  // publishes the fix-ups decided by the last tile's bookkeeping
+  // the fix-ups decided during the last tile's stage 2 were published by its S4
 #pragma unroll
   for (int f = 0; f < 2; ++f) {
     const FixEntry fx = s_fix[f];
@@ -417,7 +533,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
   }
   __syncthreads();
   for (;;) {
-    if (tid == 0) {
+    if (sched) {
       s_fix[0].tile = -2;  // -2: ring empty
       if (ring_count > 0) {
         const int bt = s_pend_bt[ring_head];

@@ -19,15 +19,20 @@ void codelet_tile_power(const float* sig, float* power) {
   }
   alignas(16) static float skew[5360 + 2 * (5360 / 160) + 8];
   static float zbuf[kZPlanes * 16 * kTileF];
-  static float pbuf[kPRows * kPStride];
+  static float pbuf[kBins * kPStride];
   memset(pbuf, 0, sizeof(pbuf));
   for (int i = 0; i < 5360; ++i) skew[i + 2 * (i / kHop)] = sig[i];
   for (int lane = 0; lane < 32; ++lane)
     for (int w = 0; w < 8; ++w)
       stage1_pair(skew + (kHop + 2) * lane, reinterpret_cast<const float4*>(cst) + w * kS1ConstVec, 2 * w, zbuf + lane);
   for (int lane = 0; lane < 32; ++lane) {
-    for (int a = 1; a < 13; a += 2) stage2_pair(zbuf + lane, a, pbuf + lane);
-    stage2_k0(zbuf + lane, pbuf + lane);
+    f2 pw[16];
+    for (int a = 1; a < 13; a += 2) {
+      stage2_pair_compute(zbuf + lane, a, pw);
+      stage2_pair_store(pw, a, pbuf + lane);
+    }
+    stage2_k0_compute(zbuf + lane, pw);
+    stage2_k0_store(pw, pbuf + lane);
   }
   for (int k = 0; k < kBins; ++k) memcpy(power + k * 32, pbuf + k * kPStride, 32 * sizeof(float));
 }
