@@ -117,8 +117,17 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
 __device__ __forceinline__ void red_max_u32(uint32_t* p, uint32_t v) {
   asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void red_release_add_u32(uint32_t* p, uint32_t v) {
-  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void red_add_u32(uint32_t* p, uint32_t v) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// named barrier over the first `nthreads` threads' warps (id 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -245,13 +254,17 @@ __device__ __forceinline__ TileDesc make_desc(const LogmelParams& p, uint32_t id
   return d;
 }
 
-// asynchronous staging of an interior float32 tile: 2680 8-byte cp.async per tile, no registers held
+// asynchronous staging of an interior float32 tile: 2680 8-byte cp.async, no registers held.  Threads 0..239 each own
+// one float2 column of three hop rows per pass, so every address is (per-thread base) + (compile-time constant).
 __device__ __forceinline__ void prefetch_signal(float* __restrict__ sig, const float* __restrict__ src, int tid) {
+  if (tid >= 240) return;
+  const int r0 = tid / 80, c = tid - 80 * r0;
+  float* d = sig + r0 * kSigStride + 2 * c;
+  const float* g = src + r0 * kHop + 2 * c;
+  constexpr int kRows = kSigLen / kHop;  // 33 full rows + half a row
 #pragma unroll
-  for (int k = 0; k < (kSigLen / 2 + kThreads - 1) / kThreads; ++k) {
-    const int j = tid + k * kThreads;  // float2 index
-    if (j < kSigLen / 2) cp_async8(sig + 2 * j + 2 * (j / (kHop / 2)), src + 2 * j);
-  }
+  for (int k = 0; k < kRows / 3; ++k) cp_async8(d + 3 * k * kSigStride, g + 3 * k * kHop);
+  if (r0 == 0 && c < (kSigLen - kRows * kHop) / 2) cp_async8(d + kRows * kSigStride, g + kRows * kHop);
 }
 
 template <typename T>
@@ -291,9 +304,13 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
     prefetch_signal(sigbuf, reinterpret_cast<const float*>(p.pcm) + cur.off + cur.tile * kTileF * kHop - kNFft / 2, tid);
   cp_async_commit();
 
-  // scheduler-lane state: pending ring, previous tile (bookkeeping is deferred by one tile)
+  // scheduler-lane state: pending ring; the previous tile (its clip max is published one tile late) and the one before
+  // (its ticket is published two tiles late, after the fence that opens the next scheduler block: no fence ever waits
+  // on an operation issued in the same block); ticket values of the two oldest pending tiles, loaded one tile ago
   int ring_head = 0, ring_count = 0;
-  int prev_b = -1, prev_tile = 0, prev_silent = 0;
+  int prev_b = -1, prev_tile = 0, prev_silent = 0, prev2_b = -1;
+  int chk0 = -1, chk1 = -1;  // clips whose tickets were requested last tile (-1: none)
+  uint32_t tk0 = 0, tk1 = 0;
   int it = 0;
 
   while (cur.b >= 0) {
@@ -348,18 +365,31 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
         stage2_k0_compute(zbuf + lane, pw);
     }
     if (sched) {
-      // tickets of the two oldest pending tiles (issued first: independent of everything below)
-      uint32_t tk0 = 0, tk1 = 0;
-      int pb0 = -1, pb1 = -1;
-      if (ring_count > 0) {
-        pb0 = s_pend_bt[ring_head] / p.ntiles;
-        tk0 = ld_acquire_u32(p.clip_ticket + pb0);
+      // (1) one fence per tile orders last tile's relaxed operations before this tile's: ticket loads -> key loads
+      //     (acquire side), clip-max RED -> ticket RED (release side).  Nothing issued in this block is waited on.
+      __threadfence();
+      if (prev2_b >= 0) red_add_u32(p.clip_ticket + prev2_b, 1u);
+      prev2_b = prev_b;
+      // (2) fix-ups for the next tile's S1, decided from the tickets requested one tile ago
+      int nfix = 0;
+      if (chk0 >= 0 && tk0 == (uint32_t)p.ntiles) {
+        const float floor_y = key2f(__ldcg(p.clip_key + chk0)) - 2.0f;
+        const int bt = s_pend_bt[ring_head];
+        const float pm = s_pend_min[ring_head];
+        ring_head = (ring_head + 1) & (kRing - 1);
+        --ring_count;
+        if (pm < floor_y) s_fix[nfix++] = FixEntry{chk0, bt - chk0 * p.ntiles, floor_y, pm == kNegInf};
+        if (chk1 >= 0 && tk1 == (uint32_t)p.ntiles) {
+          const float floor1 = key2f(__ldcg(p.clip_key + chk1)) - 2.0f;
+          const int bt1 = s_pend_bt[ring_head];
+          const float pm1 = s_pend_min[ring_head];
+          ring_head = (ring_head + 1) & (kRing - 1);
+          --ring_count;
+          if (pm1 < floor1) s_fix[nfix++] = FixEntry{chk1, bt1 - chk1 * p.ntiles, floor1, pm1 == kNegInf};
+        }
       }
-      if (ring_count > 1) {
-        pb1 = s_pend_bt[(ring_head + 1) & (kRing - 1)] / p.ntiles;
-        tk1 = ld_acquire_u32(p.clip_ticket + pb1);
-      }
-      // publish the previous tile: clip max, then the ticket (release orders the two)
+      for (int f = nfix; f < 2; ++f) s_fix[f].tile = -1;
+      // (3) previous tile: publish its clip max, remember it in the ring
       if (prev_b >= 0) {
         float mx = -1.5f, mn = kNegInf;  // silent: max = (log10(1e-10)+4)/4, min marker = -inf
         if (!prev_silent) {
@@ -373,9 +403,9 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
           }
         }
         red_max_u32(p.clip_key + prev_b, f2key(mx));
-        red_release_add_u32(p.clip_ticket + prev_b, 1u);
         // ring full: cannot happen while ntiles <= kRing unless other CTAs lag a whole clip behind; the oldest entry's
-        // clip then has every tile assigned to a RUNNING CTA (ids are handed out in order), so this wait terminates
+        // clip then has every tile assigned to a RUNNING CTA (ids are handed out in order) whose scheduler publishes
+        // before it ever waits, so this wait terminates
         if (ring_count == kRing) {
           const int bt = s_pend_bt[ring_head];
           const float pm = s_pend_min[ring_head];
@@ -389,9 +419,6 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
             for (int l = 0; l < 32; ++l)
               for (int w = 0; w < kWarps; ++w) fix_tile(p.out, p.n_mel, p.n_frames, fx, w, l);
           }
-          pb0 = pb1;  // the head moved: only the entry that was second is still a candidate
-          tk0 = tk1;
-          pb1 = -1;
         }
         const int slot = (ring_head + ring_count) & (kRing - 1);
         s_pend_bt[slot] = prev_b * p.ntiles + prev_tile;
@@ -401,46 +428,44 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
       prev_b = b;
       prev_tile = tile;
       prev_silent = silent;
-      // fix-ups for the next tile's S1, decided from the tickets read above
-      int nfix = 0;
-      if (pb0 >= 0 && tk0 == (uint32_t)p.ntiles) {
-        const float floor_y = key2f(__ldcg(p.clip_key + pb0)) - 2.0f;
-        const int bt = s_pend_bt[ring_head];
-        const float pm = s_pend_min[ring_head];
-        ring_head = (ring_head + 1) & (kRing - 1);
-        --ring_count;
-        if (pm < floor_y) s_fix[nfix++] = FixEntry{pb0, bt - pb0 * p.ntiles, floor_y, pm == kNegInf};
-        if (pb1 >= 0 && tk1 == (uint32_t)p.ntiles) {
-          const float floor1 = key2f(__ldcg(p.clip_key + pb1)) - 2.0f;
-          const int bt1 = s_pend_bt[ring_head];
-          const float pm1 = s_pend_min[ring_head];
-          ring_head = (ring_head + 1) & (kRing - 1);
-          --ring_count;
-          if (pm1 < floor1) s_fix[nfix++] = FixEntry{pb1, bt1 - pb1 * p.ntiles, floor1, pm1 == kNegInf};
-        }
+      // (4) request the tickets of the two oldest pending tiles; looked at one tile from now
+      chk0 = chk1 = -1;
+      if (ring_count > 0) {
+        chk0 = s_pend_bt[ring_head] / p.ntiles;
+        tk0 = ld_relaxed_u32(p.clip_ticket + chk0);
       }
-      for (int f = nfix; f < 2; ++f) s_fix[f].tile = -1;
-      s_desc[it & 1] = make_desc<T>(p, id2);  // tile it+2 (slot of tile it, whose descriptor is in registers)
+      if (ring_count > 1) {
+        chk1 = s_pend_bt[(ring_head + 1) & (kRing - 1)] / p.ntiles;
+        tk1 = ld_relaxed_u32(p.clip_ticket + chk1);
+      }
+      // (5) descriptor of tile it+2 (slot of tile it, whose descriptor is in registers)
+      s_desc[it & 1] = make_desc<T>(p, id2);
     }
 
     if (!silent) {
-      __syncthreads();  // S2b: every warp has read its z planes; the power buffer may now overwrite them
-      if (warp < 6)
-        stage2_pair_store(pw, 2 * warp + 1, zbuf + lane);
-      else if (warp == 6)
-        stage2_k0_store(pw, zbuf + lane);
+      if (warp < 7) {
+        bar_sync_named(1, 7 * 32);  // S2b (warps 0..6): all z planes have been read; the power buffer may overwrite them
+        if (warp < 6)
+          stage2_pair_store(pw, 2 * warp + 1, zbuf + lane);
+        else
+          stage2_k0_store(pw, zbuf + lane);
+      }
       __syncthreads();  // S3
       // ---- stage 3: banded mel projection with mma.sync TF32, epilogue log10 / scale / store ----
       {
         const int g = lane >> 2, t = lane & 3;
-        // this thread's output columns: frames mt+g, mt+g+8; rows: mels nb+2t, nb+2t+1
-        float* const out_lane = p.out + ((size_t)b * p.n_mel + 2 * t) * p.n_frames + t0 + g;
+        const int mt = (warp & 1) * 16;  // units come in (frames 0..15, frames 16..31) pairs per 8-mel tile
+        // this thread's outputs per unit: frames mt+g, mt+g+8 (columns) x mels nb+2t, nb+2t+1 (rows); a warp's units
+        // are 8 apart, i.e. 4 mel tiles = 32 rows apart: two running row pointers, no per-unit multiplies
+        float* q0 = p.out + ((size_t)b * p.n_mel + 4 * (warp >> 1) * 2 + 2 * t) * p.n_frames + t0 + mt + g;
+        const size_t row = (size_t)p.n_frames, step = 32 * row;
         const bool full = nvalid == kTileF;
-        for (int u = warp; u < p.n_units; u += kWarps) {
-          const int4 mu = *reinterpret_cast<const int4*>(&s_units[u]);  // kstep0, ks, kb, nb
-          const int mt = (u & 1) * 16;  // units come in (frames 0..15, frames 16..31) pairs per 8-mel tile
+        const int4* up = reinterpret_cast<const int4*>(s_units) + warp;
+        const float* abase = zbuf + t * kPStride + mt + g;
+        for (int u = warp; u < p.n_units; u += kWarps, up += kWarps, q0 += step) {
+          const int4 mu = *up;  // kstep0, ks, kb, nb
           float acc[4] = {0.f, 0.f, 0.f, 0.f};
-          const float* arow = zbuf + (mu.z + t) * kPStride + mt + g;
+          const float* arow = abase + mu.z * kPStride;
           const float2* brow = s_btab + mu.x * 32 + lane;
 #pragma unroll 2
           for (int s = 0; s < mu.y; ++s) {
@@ -459,21 +484,21 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
           // c0: (frame mt+g, mel nb+2t)  c1: (mt+g, nb+2t+1)  c2: (mt+g+8, nb+2t)  c3: (mt+g+8, nb+2t+1)
           const float y0 = logmel_feature(acc[0]), y1 = logmel_feature(acc[1]);
           const float y2 = logmel_feature(acc[2]), y3 = logmel_feature(acc[3]);
-          float* q = out_lane + (size_t)mu.w * p.n_frames + mt;
+          float* q1 = q0 + row;
           if (full && mu.w + 8 <= p.n_mel) {
-            q[0] = y0;
-            q[p.n_frames] = y1;
-            q[8] = y2;
-            q[p.n_frames + 8] = y3;
+            q0[0] = y0;
+            q1[0] = y1;
+            q0[8] = y2;
+            q1[8] = y3;
             tmax_y = fmaxf(tmax_y, fmaxf(fmaxf(y0, y1), fmaxf(y2, y3)));
             tmin_y = fminf(tmin_y, fminf(fminf(y0, y1), fminf(y2, y3)));
           } else {
             const bool f0 = mt + g < nvalid, f1 = mt + g + 8 < nvalid;
             const bool m0 = mu.w + 2 * t < p.n_mel, m1 = mu.w + 2 * t + 1 < p.n_mel;
-            if (f0 && m0) { q[0] = y0; tmax_y = fmaxf(tmax_y, y0); tmin_y = fminf(tmin_y, y0); }
-            if (f0 && m1) { q[p.n_frames] = y1; tmax_y = fmaxf(tmax_y, y1); tmin_y = fminf(tmin_y, y1); }
-            if (f1 && m0) { q[8] = y2; tmax_y = fmaxf(tmax_y, y2); tmin_y = fminf(tmin_y, y2); }
-            if (f1 && m1) { q[p.n_frames + 8] = y3; tmax_y = fmaxf(tmax_y, y3); tmin_y = fminf(tmin_y, y3); }
+            if (f0 && m0) { q0[0] = y0; tmax_y = fmaxf(tmax_y, y0); tmin_y = fminf(tmin_y, y0); }
+            if (f0 && m1) { q1[0] = y1; tmax_y = fmaxf(tmax_y, y1); tmin_y = fminf(tmin_y, y1); }
+            if (f1 && m0) { q0[8] = y2; tmax_y = fmaxf(tmax_y, y2); tmin_y = fminf(tmin_y, y2); }
+            if (f1 && m1) { q1[8] = y3; tmax_y = fmaxf(tmax_y, y3); tmin_y = fminf(tmin_y, y3); }
           }
         }
       }
@@ -496,32 +521,37 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
 
   // ---- epilogue: publish the last tile, then drain the tiles this CTA still has pending (every remaining tile of
   //      their clips is owned by a running CTA, so the waits terminate) ----
-  if (sched && prev_b >= 0) {
-    float mx = -1.5f, mn = kNegInf;
-    if (!prev_silent) {
-      const int pp = (it + 1) & 1;
-      mx = s_red[pp][0][0];
-      mn = s_red[pp][1][0];
+  if (sched) {
+    __threadfence();
+    if (prev2_b >= 0) red_add_u32(p.clip_ticket + prev2_b, 1u);
+    if (prev_b >= 0) {
+      float mx = -1.5f, mn = kNegInf;
+      if (!prev_silent) {
+        const int pp = (it + 1) & 1;
+        mx = s_red[pp][0][0];
+        mn = s_red[pp][1][0];
 #pragma unroll
-      for (int w = 1; w < kWarps; ++w) {
-        mx = fmaxf(mx, s_red[pp][0][w]);
-        mn = fminf(mn, s_red[pp][1][w]);
+        for (int w = 1; w < kWarps; ++w) {
+          mx = fmaxf(mx, s_red[pp][0][w]);
+          mn = fminf(mn, s_red[pp][1][w]);
+        }
       }
-    }
-    red_max_u32(p.clip_key + prev_b, f2key(mx));
-    red_release_add_u32(p.clip_ticket + prev_b, 1u);
-    if (ring_count < kRing) {
-      const int slot = (ring_head + ring_count) & (kRing - 1);
-      s_pend_bt[slot] = prev_b * p.ntiles + prev_tile;
-      s_pend_min[slot] = mn;
-      ++ring_count;
-    } else {  // ring full (see above): fix this one serially once its clip completes
-      while (ld_acquire_u32(p.clip_ticket + prev_b) != (uint32_t)p.ntiles) __nanosleep(200);
-      const float fl = key2f(__ldcg(p.clip_key + prev_b)) - 2.0f;
-      if (mn < fl) {
-        const FixEntry fx{prev_b, prev_tile, fl, mn == kNegInf};
-        for (int l = 0; l < 32; ++l)
-          for (int w = 0; w < kWarps; ++w) fix_tile(p.out, p.n_mel, p.n_frames, fx, w, l);
+      red_max_u32(p.clip_key + prev_b, f2key(mx));
+      __threadfence();
+      red_add_u32(p.clip_ticket + prev_b, 1u);
+      if (ring_count < kRing) {
+        const int slot = (ring_head + ring_count) & (kRing - 1);
+        s_pend_bt[slot] = prev_b * p.ntiles + prev_tile;
+        s_pend_min[slot] = mn;
+        ++ring_count;
+      } else {  // ring full (see above): fix this one serially once its clip completes
+        while (ld_acquire_u32(p.clip_ticket + prev_b) != (uint32_t)p.ntiles) __nanosleep(200);
+        const float fl = key2f(__ldcg(p.clip_key + prev_b)) - 2.0f;
+        if (mn < fl) {
+          const FixEntry fx{prev_b, prev_tile, fl, mn == kNegInf};
+          for (int l = 0; l < 32; ++l)
+            for (int w = 0; w < kWarps; ++w) fix_tile(p.out, p.n_mel, p.n_frames, fx, w, l);
+        }
       }
     }
   }
