@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwfe.so")
+LIB_PATH = os.environ.get("WFE_LIB_OVERRIDE") or os.path.join(_HERE, "libwfe.so")  # override: timing what-if builds
 
 WFE_PCM_F32, WFE_PCM_I16 = 0, 1
 

@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <new>
@@ -73,11 +74,12 @@ struct HostSlot {
 
 struct wfe_handle {
   wfe_config cfg;
-  int n_frames = 0, ntiles = 0, n_units = 0, n_ksteps = 0, sm_count = 0;
+  int n_frames = 0, ntiles = 0, n_groups = 0, n_rows = 0, sm_count = 0;
+  int mel_wrange[wfe::kWarps + 1] = {0};
   int ctas_per_sm[2] = {0, 0};   // resident CTAs of logmel_kernel<float>, <int16_t>
   float4* d_s1_consts = nullptr;       // [8][25]
-  float2* d_mel_btab = nullptr;        // [n_ksteps][32]
-  wfe::MelUnit* d_mel_units = nullptr; // [n_units]
+  int4* d_mel_tab = nullptr;             // [n_rows][2][2]
+  wfe::MelGroup* d_mel_groups = nullptr; // [n_groups]
   std::mutex host_mu;
   bool ring_ready = false;
   int chunk_clips = 16;
@@ -86,18 +88,8 @@ struct wfe_handle {
 
 namespace {
 
-// round-to-nearest (ties away) fp32 -> tf32, like cvt.rna.tf32.f32
-float tf32_rna(float x) {
-  uint32_t u;
-  memcpy(&u, &x, 4);
-  u = (u + 0x1000u) & 0xffffe000u;
-  float r;
-  memcpy(&r, &u, 4);
-  return r;
-}
-
 size_t scratch_bytes(const wfe_handle*, int batch) {
-  // clip_key[B], clip_ticket[B], tile_counter (+ pad to 16 B)
+  // clip_state[B] = {max key, ticket} (8 B each), tile_counter (+ pad to 16 B)
   return ((size_t)batch * 2 + 4) * sizeof(uint32_t);
 }
 
@@ -114,28 +106,31 @@ int launch_logmel(wfe_handle* h, const void* pcm, float scale, const int64_t* of
   p.norm = reinterpret_cast<const float2*>(norm);
   p.out = out;
   p.mask = mask;
-  p.clip_key = reinterpret_cast<uint32_t*>(scratch);
-  p.clip_ticket = p.clip_key + batch;
-  p.tile_counter = p.clip_ticket + batch;
+  if ((reinterpret_cast<uintptr_t>(scratch) & 7u) != 0) return fail(WFE_ERR_INVALID, "scratch must be 8-byte aligned");
+  p.clip_state = reinterpret_cast<uint2*>(scratch);
+  p.tile_counter = reinterpret_cast<uint32_t*>(scratch) + 2 * (size_t)batch;
   p.s1_consts = h->d_s1_consts;
-  p.mel_btab = h->d_mel_btab;
-  p.mel_units = h->d_mel_units;
+  p.mel_tab = h->d_mel_tab;
+  p.mel_groups = h->d_mel_groups;
+  for (int w = 0; w <= wfe::kWarps; ++w) p.mel_wrange[w] = h->mel_wrange[w];
   p.pcm_scale = scale;
   p.n_mel = h->cfg.n_mel;
   p.n_samples = h->cfg.n_samples;
   p.n_frames = h->n_frames;
   p.ntiles = h->ntiles;
-  p.n_units = h->n_units;
-  p.n_ksteps = h->n_ksteps;
+  p.n_groups = h->n_groups;
+  p.n_rows = h->n_rows;
   p.total_tiles = (uint32_t)total;
   WFE_CUDA(cudaMemsetAsync(scratch, 0, scratch_bytes(h, batch), st));
-  const size_t smem = wfe::logmel_smem_bytes(h->n_ksteps);
+  const size_t smem = wfe::logmel_smem_bytes(h->n_rows);
   const int which = sizeof(T) == 4 ? 0 : 1;
   if (h->ctas_per_sm[which] == 0) {
-    // opt in to > 48 KB dynamic shared memory (per function, shared by every handle: always the maximum any filter
-    // bank can need) and size the persistent grid from the real occupancy
+    // opt in to > 48 KB dynamic shared memory (the attribute is per function, shared by every handle: set it to the
+    // most any filter bank can need) and size the persistent grid from the real occupancy
     WFE_CUDA(cudaFuncSetAttribute(wfe::logmel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)wfe::logmel_smem_bytes(wfe::kMaxKsteps)));
+                                  (int)wfe::logmel_smem_bytes(wfe::kMaxMelRows)));
+    WFE_CUDA(cudaFuncSetAttribute(wfe::logmel_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  cudaSharedmemCarveoutMaxShared));
     int n = 0;
     WFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, wfe::logmel_kernel<T>, wfe::kThreads, smem));
     if (n < 1) return fail(WFE_ERR_CUDA, "logmel kernel does not fit on an SM");
@@ -259,62 +254,104 @@ int wfe_create(const wfe_config* cfg, const float* mel_filters, wfe_handle** out
   }
   h->sm_count = prop.multiProcessorCount;
 
-  // ---- mel projection tables: the filter bank is banded, so only the non-zero 8-mel x 8-bin blocks are kept ----
-  // n-tile j = mels [8j, 8j+8); its k-steps cover bins [lo_j, hi_j] in chunks of 8; B fragments of mma.m16n8k8 (col):
-  //   lane (g = lane/4, t = lane%4): b0 = F[kb+t][8j+g], b1 = F[kb+t+4][8j+g], pre-rounded to TF32.
-  const int n_mel = cfg->n_mel, n_tiles_n = (n_mel + 7) / 8;
-  std::vector<float2> btab;
-  std::vector<wfe::MelUnit> units;
-  auto F = [&](int k, int m) -> float {
-    return (k >= 0 && k < wfe::kBins && m < n_mel) ? mel_filters[(size_t)k * n_mel + m] : 0.0f;
+  // ---- mel projection tables (banded filter bank).  Mels are taken two at a time (m, m+1: one per half-warp); pairs
+  // are sorted by non-zero count and cut into groups of four "slots" that run in lock step over a common number of
+  // table rows (zero-weight padding up to the group's longest filter), so each thread carries four independent
+  // accumulators.  A table row holds, per half and slot, (float offset of the bin's row in the power buffer, weight).
+  const int n_mel = cfg->n_mel;
+  struct Nz {
+    int k;
+    float w;
   };
-  for (int j = 0; j < n_tiles_n; ++j) {
-    int lo = wfe::kBins, hi = -1;
-    for (int k = 0; k < wfe::kBins; ++k)
-      for (int m = 8 * j; m < 8 * j + 8 && m < n_mel; ++m)
-        if (F(k, m) != 0.0f) {
-          lo = k < lo ? k : lo;
-          hi = k > hi ? k : hi;
-        }
-    wfe::MelUnit u;
-    u.kstep0 = (int32_t)(btab.size() / 32);
-    u.nb = 8 * j;
-    if (hi < 0) {  // all-zero filters: one k-step of zeros keeps the epilogue (log10(1e-10)) uniform
-      lo = 0;
-      hi = 0;
+  std::vector<std::vector<Nz>> nz(n_mel + 1);
+  for (int m = 0; m < n_mel; ++m)
+    for (int k = 0; k < wfe::kBins; ++k) {
+      const float w = mel_filters[(size_t)k * n_mel + m];
+      if (w != 0.0f) nz[m].push_back({k, w});
     }
-    u.ks = (hi - lo + 8) / 8;
-    // the k-steps may start below `lo` (zero weights there) so that they end at bin 200 at the latest: the power
-    // buffer has exactly 201 rows
-    u.kb = lo < wfe::kBins - 8 * u.ks ? lo : wfe::kBins - 8 * u.ks;
-    for (int s = 0; s < u.ks; ++s)
-      for (int lane = 0; lane < 32; ++lane) {
-        const int g = lane >> 2, t = lane & 3, kb = u.kb + 8 * s;
-        // the kernel feeds the power values to the tensor core untouched, i.e. TRUNCATED to tf32 (relative error in
-        // (-2^-10, 0]); scaling the weights by 1 + 2^-11 centres that error at (-2^-11, 2^-11)
-        const float bias = 1.0f + 1.0f / 2048.0f;
-        btab.push_back(make_float2(tf32_rna(F(kb + t, 8 * j + g) * bias), tf32_rna(F(kb + t + 4, 8 * j + g) * bias)));
-      }
-    units.push_back(u);  // frames  0..15 of the tile
-    units.push_back(u);  // frames 16..31
+  struct PairN {
+    int m, n;
+  };
+  std::vector<PairN> prs;
+  for (int m = 0; m < n_mel; m += 2) {
+    const int n = (int)(nz[m].size() > nz[m + 1].size() ? nz[m].size() : nz[m + 1].size());
+    prs.push_back({m, n});
   }
-  h->n_units = (int)units.size();
-  h->n_ksteps = (int)(btab.size() / 32);
-  if (h->n_units > wfe::kMaxUnits || h->n_ksteps > wfe::kMaxKsteps) {
+  std::sort(prs.begin(), prs.end(), [](const PairN& a, const PairN& b) { return a.n != b.n ? a.n > b.n : a.m < b.m; });
+  struct GroupCost {
+    int first, cost;  // first pair (index into prs), issue-slot estimate
+  };
+  std::vector<GroupCost> gpool;
+  for (size_t i = 0; i < prs.size(); i += 4) gpool.push_back({(int)i, 14 * (prs[i].n < 1 ? 1 : prs[i].n) + 50});
+  std::vector<std::vector<int>> per_warp(wfe::kWarps);
+  int load[wfe::kWarps] = {0};
+  for (const GroupCost& gc : gpool) {  // longest-processing-time first (gpool is already sorted by cost, descending)
+    int w = 0;
+    for (int i = 1; i < wfe::kWarps; ++i)
+      if (load[i] < load[w]) w = i;
+    per_warp[w].push_back(gc.first);
+    load[w] += gc.cost;
+  }
+  std::vector<int4> mtab;
+  std::vector<wfe::MelGroup> groups;
+  for (int w = 0; w < wfe::kWarps; ++w) {
+    h->mel_wrange[w] = (int)groups.size();
+    for (int first : per_warp[w]) {
+      wfe::MelGroup g;
+      g.trips = prs[first].n < 1 ? 1 : prs[first].n;
+      g.tab_idx = (int32_t)mtab.size();
+      g.valid = 0;
+      g.pad_ = 0;
+      int mel_of[4];
+      for (int sl = 0; sl < 4; ++sl) {
+        const bool real = first + sl < (int)prs.size();
+        mel_of[sl] = real ? prs[first + sl].m : -1;
+        g.out_off[sl] = real ? mel_of[sl] * h->n_frames : 0;
+        if (real) g.valid |= 1 << (2 * sl);
+        if (real && mel_of[sl] + 1 < n_mel) g.valid |= 1 << (2 * sl + 1);
+      }
+      for (int i = 0; i < g.trips; ++i)
+        for (int half = 0; half < 2; ++half)
+          for (int sp = 0; sp < 2; ++sp) {  // one int4 = slots 2sp, 2sp+1
+            int4 row;
+            int* r = &row.x;
+            for (int j = 0; j < 2; ++j) {
+              const int sl = 2 * sp + j;
+              int k = 0;
+              float wgt = 0.0f;
+              if (mel_of[sl] >= 0) {
+                const std::vector<Nz>& v = nz[mel_of[sl] + half];
+                if (i < (int)v.size()) {
+                  k = v[i].k;
+                  wgt = v[i].w;
+                }
+              }
+              r[2 * j] = k * wfe::kPStride;
+              memcpy(&r[2 * j + 1], &wgt, sizeof(float));
+            }
+            mtab.push_back(row);
+          }
+      groups.push_back(g);
+    }
+  }
+  h->mel_wrange[wfe::kWarps] = (int)groups.size();
+  h->n_groups = (int)groups.size();
+  h->n_rows = (int)(mtab.size() / 4);
+  if (h->n_groups > wfe::kMaxMelGroups || h->n_rows > wfe::kMaxMelRows) {
     delete h;
-    return fail(WFE_ERR_UNSUPPORTED, "mel filter bank is not banded enough for the tensor-pipe projection");
+    return fail(WFE_ERR_UNSUPPORTED, "mel filter bank has too many non-zeros (not banded)");
   }
   std::vector<float> s1c(8 * wfe::kS1ConstVec * 4);
   wfe::fill_stage1_consts(s1c.data());
   if (cudaMalloc((void**)&h->d_s1_consts, s1c.size() * sizeof(float)) != cudaSuccess ||
-      cudaMalloc((void**)&h->d_mel_btab, btab.size() * sizeof(float2)) != cudaSuccess ||
-      cudaMalloc((void**)&h->d_mel_units, units.size() * sizeof(wfe::MelUnit)) != cudaSuccess) {
+      cudaMalloc((void**)&h->d_mel_tab, mtab.size() * sizeof(int4)) != cudaSuccess ||
+      cudaMalloc((void**)&h->d_mel_groups, groups.size() * sizeof(wfe::MelGroup)) != cudaSuccess) {
     wfe_destroy(h);
     return fail(WFE_ERR_NOMEM, "cudaMalloc failed for constant tables");
   }
   cudaMemcpy(h->d_s1_consts, s1c.data(), s1c.size() * sizeof(float), cudaMemcpyHostToDevice);
-  cudaMemcpy(h->d_mel_btab, btab.data(), btab.size() * sizeof(float2), cudaMemcpyHostToDevice);
-  cudaMemcpy(h->d_mel_units, units.data(), units.size() * sizeof(wfe::MelUnit), cudaMemcpyHostToDevice);
+  cudaMemcpy(h->d_mel_tab, mtab.data(), mtab.size() * sizeof(int4), cudaMemcpyHostToDevice);
+  cudaMemcpy(h->d_mel_groups, groups.data(), groups.size() * sizeof(wfe::MelGroup), cudaMemcpyHostToDevice);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     wfe_destroy(h);
@@ -329,8 +366,8 @@ void wfe_destroy(wfe_handle* h) {
   DeviceGuard guard(h->cfg.device);
   free_ring(h);
   if (h->d_s1_consts) cudaFree(h->d_s1_consts);
-  if (h->d_mel_btab) cudaFree(h->d_mel_btab);
-  if (h->d_mel_units) cudaFree(h->d_mel_units);
+  if (h->d_mel_tab) cudaFree(h->d_mel_tab);
+  if (h->d_mel_groups) cudaFree(h->d_mel_groups);
   delete h;
 }
 

@@ -236,9 +236,9 @@ WFE_DEV void dft16_power(const cx<T> (&z)[16], T (&pw)[16]) {
 constexpr int kZPlanes = 25;
 WFE_DEV int z_plane(int k2, int im) { return k2 == 0 ? 0 : 1 + 2 * (k2 - 1) + im; }
 WFE_DEV int z_index(int plane, int n1, int frame) { return (plane * 16 + n1) * kTileF + frame; }
-// power buffer (stage 2 -> mel): BIN-major, 201 rows with a stride of 40 floats: conflict-free [row][lane] stores in
-// stage 2 and conflict-free mma.sync A-fragment loads (bank = 8*(k%4) + frame%8) in the mel stage.
-constexpr int kPStride = 40;
+// power buffer (stage 2 -> mel): BIN-major, 201 rows of 32 frames: conflict-free [row][lane] stores in stage 2 and
+// conflict-free 64-bit loads of (frame 2p, frame 2p+1) pairs in the mel stage.
+constexpr int kPStride = 32;
 // bin computed by stage 2 for residue k2 (0..12) and output index k1 (0..15): 25*k1 + k2, folded by conjugate symmetry
 inline int stage2_bin(int k2, int k1) {
   const int k = 25 * k1 + k2;

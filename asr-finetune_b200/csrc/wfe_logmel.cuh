@@ -10,9 +10,10 @@
 //            packed f32x2 (FADD2/FMUL2/FFMA2)                                                    (steps 5-6)
 //   stage 2  6 warps x (k2, k2+1) + 1 warp for k2 = 0: complex 16-point DFT (4x4) over n1, power |X|^2, stored
 //            bin-major                                                                           (steps 6-7)
-//   stage 3  mel projection on the tensor pipe: the slaney filter bank is banded (33 non-zero 8-mel x 8-bin blocks of
-//            26 x 16), so each warp issues a handful of mma.sync m16n8k8 TF32 (frames x bins x mels) with the filter
-//            fragments read from smem; epilogue log10, (x+4)/4, store, tile min/max              (steps 8, 9, 11)
+//   stage 3  banded slaney mel projection in exact fp32: each half-warp owns one mel and 16 frame PAIRS, so one
+//            LDS.64 (power of two adjacent frames) + one FFMA2 with the weight broadcast covers two frames of a
+//            non-zero; epilogue log10, (x+4)/4, full-line 64-bit stores, tile min/max            (steps 8, 9, 11)
+//            (legacy mma.sync TF32 was tried and measured at CUDA-core rate on B200 - see DESIGN.md)
 //   clamp    per-clip max-8 clamp (step 10) without a second pass over HBM: every CTA remembers its own tiles and,
 //            once the clip's ticket shows all of its tiles are done, re-reads only the tiles whose minimum is below
 //            the floor from L2 and fixes them; tiles that lie entirely in the zero padding are written once, late.
@@ -26,6 +27,11 @@
 
 #include "wfe_codelets.cuh"
 
+#ifndef WFE_EXP
+#define WFE_EXP 0  // bit 0: skip clamp fix-ups, bit 1: skip mel stage, bit 2: skip stage 2, bit 3: skip stage 1,
+                   // bit 4: skip scheduler bookkeeping (what-if timing builds only: results are wrong)
+#endif
+
 namespace wfe {
 
 constexpr int kWarps = 8;
@@ -35,8 +41,8 @@ constexpr int kSigStride = kHop + 2;                  // +2 pad words per 160 sa
 constexpr int kSigSm = kSigLen + 2 * (kSigLen / kHop) + 4;   // 5430 floats per staging buffer (two of them)
 constexpr int kZSm = kZPlanes * 16 * kTileF;          // 12800 floats; the power buffer (201 x 40) aliases it
 constexpr int kRing = 128;                            // pending-tile ring (>= tiles per clip, see wfe_api.cu)
-constexpr int kMaxUnits = 64;                         // (8-mel tile, 16-frame tile) work units of the mel stage
-constexpr int kMaxKsteps = 64;                        // non-zero 8x8 blocks of the filter bank (33 for Whisper)
+constexpr int kMaxMelGroups = 32;                     // groups of 4 mel pairs (n_mel <= 256)
+constexpr int kMaxMelRows = 256;                      // table rows over all groups (55 for large-v3, 54 for whisper-small)
 
 static_assert(kBins * kPStride <= kZSm, "power buffer must fit in the z buffer it aliases");
 static_assert((kSigSm * 4) % 16 == 0 || true, "");
@@ -57,12 +63,15 @@ __device__ __forceinline__ float pcm_to_float<float>(float v, float) { return v;
 template <>
 __device__ __forceinline__ float pcm_to_float<int16_t>(int16_t v, float scale) { return (float)v * scale; }
 
-// one mel-stage work unit: 8 mels x 16 frames, `ks` k-steps of 8 bins starting at bin `kb`
-struct alignas(16) MelUnit {
-  int32_t kstep0;  // first k-step (index into the B-fragment table)
-  int32_t ks;      // number of k-steps
-  int32_t kb;      // first bin
-  int32_t nb;      // first mel
+// one mel-stage work item: FOUR mel pairs (slot s: mels m_s, m_s+1, one per half-warp) that run in lock step over `trips`
+// table rows, so every thread has four independent accumulator chains.  Pairs are grouped by similar non-zero counts
+// (zero-weight padding up to the group's longest filter: 220 rows for 211 real ones on the large-v3 bank).
+struct alignas(16) MelGroup {
+  int32_t trips;       // table rows
+  int32_t tab_idx;     // index (in int4 units) of the group's first row; a row is [half][slot 0..3] x (offset, weight)
+  int32_t valid;       // bit 2*s + h: mel of slot s, half h exists
+  int32_t pad_;
+  int32_t out_off[4];  // m_s * n_frames: element offset of slot s's first mel row inside one clip's output
 };
 
 struct LogmelParams {
@@ -72,20 +81,21 @@ struct LogmelParams {
   const float2* norm;       // (mean, rstd) per clip or nullptr
   float* out;               // (B, n_mel, n_frames)
   int32_t* mask;            // (B, n_frames) or nullptr
-  uint32_t* clip_key;       // [B] running max of the scaled feature y = (log10(mel)+4)/4 as ordered key (zero-init)
-  uint32_t* clip_ticket;    // [B] finished-tile counter (zero-initialised)
+  uint2* clip_state;        // [B] {x: running max of y = (log10(mel)+4)/4 as ordered key, y: finished-tile ticket};
+                            //     one 8-byte word so that a single 64-bit load sees a consistent pair (zero-init)
   uint32_t* tile_counter;   // [1] dynamic tile scheduler (zero-initialised)
   const float4* s1_consts;  // [8][25] per-warp window/twiddle block
-  const float2* mel_btab;   // [n_ksteps][32] per-lane B fragments (TF32-rounded filter weights)
-  const MelUnit* mel_units; // [n_units]
+  const int4* mel_tab;      // [n_rows][2 halves][2] : (power-row float offset, weight bits) x 4 slots per half
+  const MelGroup* mel_groups;  // [n_groups], grouped by warp
+  int mel_wrange[kWarps + 1];  // warp w owns groups [mel_wrange[w], mel_wrange[w+1])
   float pcm_scale;
-  int n_mel, n_samples, n_frames, ntiles, n_units, n_ksteps;
+  int n_mel, n_samples, n_frames, ntiles, n_groups, n_rows;
   uint32_t total_tiles;
 };
 
 constexpr int kSigBuf = (kSigSm + 3) & ~3;  // 16-byte multiple
-__host__ __device__ inline size_t logmel_smem_bytes(int n_ksteps) {
-  return (size_t)(2 * kSigBuf + kZSm) * 4 + 8 * kS1ConstVec * 16 + (size_t)n_ksteps * 32 * 8;
+__host__ __device__ inline size_t logmel_smem_bytes(int n_rows) {
+  return (size_t)(2 * kSigBuf + kZSm) * 4 + 8 * kS1ConstVec * 16 + (size_t)n_rows * 4 * 16;
 }
 
 // work item handed from the scheduler lane to the CTA through shared memory
@@ -114,6 +124,13 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// {key, ticket} of a clip in ONE 64-bit access: if the ticket it returns is complete, the key it returns is final
+// (every writer's max is performed before its ticket increment, and this load is performed at a single instant)
+__device__ __forceinline__ uint2 ld_relaxed_u64(const uint2* p) {
+  uint2 v;
+  asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void red_max_u32(uint32_t* p, uint32_t v) {
   asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -128,12 +145,6 @@ __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
 // named barrier over the first `nthreads` threads' warps (id 1..15; 0 is __syncthreads)
 __device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ float lg2_approx(float x) {
   float r;
@@ -220,23 +231,21 @@ __device__ __forceinline__ void stage_signal(float* __restrict__ sig, const T* _
   }
 }
 
-// fill a work-item descriptor for tile id `id` (scheduler lane only): clip geometry + how its signal gets staged
+// work-item descriptor for tile id `id` of a clip whose (offset, available samples) are already known
 template <typename T>
-__device__ __forceinline__ TileDesc make_desc(const LogmelParams& p, uint32_t id) {
+__device__ __forceinline__ TileDesc make_desc(const LogmelParams& p, uint32_t id, int64_t off, int64_t avail) {
   TileDesc d;
   d.pad_ = 0;
+  d.off = off;
   if (id >= p.total_tiles) {
     d.b = -1;
     d.tile = 0;
     d.len = 0;
     d.mode = kModeSilent;
-    d.off = 0;
     return d;
   }
   d.b = (int)(id / (uint32_t)p.ntiles);
   d.tile = (int)(id - (uint32_t)d.b * (uint32_t)p.ntiles);
-  d.off = __ldg(p.offsets + d.b);
-  const int64_t avail = (p.lengths != nullptr ? __ldg(p.lengths + d.b) : __ldg(p.offsets + d.b + 1) - d.off);
   d.len = (int)(avail < (int64_t)p.n_samples ? avail : (int64_t)p.n_samples);  // truncate to 30 s
   const int s_begin = d.tile * kTileF * kHop - kNFft / 2;
   const int s_hi = s_begin + kSigLen - 1;
@@ -252,6 +261,16 @@ __device__ __forceinline__ TileDesc make_desc(const LogmelParams& p, uint32_t id
     d.mode = async_ok ? kModeAsync : kModeSync;
   }
   return d;
+}
+// request (plain loads, not waited on here) the clip geometry a descriptor needs
+__device__ __forceinline__ void request_clip(const LogmelParams& p, uint32_t id, int64_t& off, int64_t& avail) {
+  off = 0;
+  avail = 0;
+  if (id < p.total_tiles) {
+    const int b = (int)(id / (uint32_t)p.ntiles);
+    off = __ldg(p.offsets + b);
+    avail = p.lengths != nullptr ? __ldg(p.lengths + b) : __ldg(p.offsets + b + 1) - off;
+  }
 }
 
 // asynchronous staging of an interior float32 tile: 2680 8-byte cp.async, no registers held.  Threads 0..239 each own
@@ -273,8 +292,8 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
   float* const sigbuf = smem;               // two signal staging buffers (tile i -> buffer i & 1)
   float* const zbuf = smem + 2 * kSigBuf;   // stage 1 -> stage 2 exchange; the power buffer aliases it after stage 2
   float4* const s_cst = reinterpret_cast<float4*>(zbuf + kZSm);
-  float2* const s_btab = reinterpret_cast<float2*>(s_cst + 8 * kS1ConstVec);
-  __shared__ MelUnit s_units[kMaxUnits];
+  int4* const s_mtab = reinterpret_cast<int4*>(s_cst + 8 * kS1ConstVec);
+  __shared__ MelGroup s_groups[kMaxMelGroups];
   __shared__ float s_red[2][2][kWarps];  // [tile parity][max, min][warp]
   __shared__ TileDesc s_desc[2];         // descriptor of tile k lives in slot k & 1
   __shared__ FixEntry s_fix[2];
@@ -285,15 +304,32 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
   const float kNegInf = -__int_as_float(0x7f800000);
   const bool sched = tid == 7 * 32;  // lane 0 of warp 7 (idle in stage 2): tile scheduler + clip bookkeeping
 
+  // scheduler-lane state.  Everything it needs from global memory is REQUESTED in one tile and CONSUMED in the next,
+  // so the lane never waits on a load; the only fence it executes finds nothing outstanding.
+  //   idA: id of tile it+2, its clip geometry (offA, availA) requested last tile -> descriptor written this tile
+  //   stA/stB: {key, ticket} of the two oldest pending tiles' clips, requested last tile
+  //   prev: the previous tile (clip max published this tile); prev2: the one before (ticket published this tile)
+  int ring_head = 0, ring_count = 0;
+  int prev_b = -1, prev_tile = 0, prev_silent = 0, prev2_b = -1;
+  int chk0 = -1, chk1 = -1;
+  uint2 st0 = make_uint2(0, 0), st1 = make_uint2(0, 0);
+  uint32_t idA = 0;
+  int64_t offA = 0, availA = 0;
+
   // ---- one-time CTA set-up ----
   for (int i = tid; i < 8 * kS1ConstVec; i += kThreads) s_cst[i] = p.s1_consts[i];
-  for (int i = tid; i < p.n_ksteps * 32; i += kThreads) s_btab[i] = p.mel_btab[i];
-  for (int i = tid; i < p.n_units; i += kThreads) s_units[i] = p.mel_units[i];
+  for (int i = tid; i < p.n_groups; i += kThreads) s_groups[i] = p.mel_groups[i];
+  for (int i = tid; i < p.n_rows * 4; i += kThreads) s_mtab[i] = p.mel_tab[i];
   if (sched) {
     const uint32_t id0 = atomicAdd(p.tile_counter, 1u);
     const uint32_t id1 = atomicAdd(p.tile_counter, 1u);
-    s_desc[0] = make_desc<T>(p, id0);
-    s_desc[1] = make_desc<T>(p, id1);
+    idA = atomicAdd(p.tile_counter, 1u);
+    int64_t o, a;
+    request_clip(p, id0, o, a);
+    s_desc[0] = make_desc<T>(p, id0, o, a);
+    request_clip(p, id1, o, a);
+    s_desc[1] = make_desc<T>(p, id1, o, a);
+    request_clip(p, idA, offA, availA);
     s_fix[0].tile = -1;
     s_fix[1].tile = -1;
   }
@@ -303,14 +339,6 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
   if (cur.b >= 0 && cur.mode == kModeAsync)
     prefetch_signal(sigbuf, reinterpret_cast<const float*>(p.pcm) + cur.off + cur.tile * kTileF * kHop - kNFft / 2, tid);
   cp_async_commit();
-
-  // scheduler-lane state: pending ring; the previous tile (its clip max is published one tile late) and the one before
-  // (its ticket is published two tiles late, after the fence that opens the next scheduler block: no fence ever waits
-  // on an operation issued in the same block); ticket values of the two oldest pending tiles, loaded one tile ago
-  int ring_head = 0, ring_count = 0;
-  int prev_b = -1, prev_tile = 0, prev_silent = 0, prev2_b = -1;
-  int chk0 = -1, chk1 = -1;  // clips whose tickets were requested last tile (-1: none)
-  uint32_t tk0 = 0, tk1 = 0;
   int it = 0;
 
   while (cur.b >= 0) {
@@ -322,8 +350,8 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
     float* const sig = sigbuf + (it & 1) * kSigBuf;
 
     // ---- top: start the NEXT tile's loads, then make sure this tile's signal has landed ----
-    uint32_t id2 = 0;
-    if (sched) id2 = atomicAdd(p.tile_counter, 1u);  // id of tile it+2, consumed in stage 2
+    uint32_t idB = 0;
+    if (sched) idB = atomicAdd(p.tile_counter, 1u);  // id of tile it+3, first used in this tile's stage 2
     if (nxt.b >= 0 && nxt.mode == kModeAsync)
       prefetch_signal(sigbuf + ((it + 1) & 1) * kSigBuf,
                       reinterpret_cast<const float*>(p.pcm) + nxt.off + nxt.tile * kTileF * kHop - kNFft / 2, tid);
@@ -342,54 +370,61 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
     __syncthreads();     // S1: signal visible to all warps; s_fix / s_desc from the previous stage 2 published
 
     // ---- clamp fix-ups decided during the previous tile (own tiles, L2-resident) ----
+    if (!(WFE_EXP & 1)) {
 #pragma unroll
-    for (int f = 0; f < 2; ++f) {
-      const FixEntry fx = s_fix[f];
-      if (fx.tile >= 0) fix_tile(p.out, p.n_mel, p.n_frames, fx, warp, lane);
+      for (int f = 0; f < 2; ++f) {
+        const FixEntry fx = s_fix[f];
+        if (fx.tile >= 0) fix_tile(p.out, p.n_mel, p.n_frames, fx, warp, lane);
+      }
     }
 
     float tmax_y = -1.5f, tmin_y = 3.0e38f;
     if (!silent) {
       // ---- stage 1: warp w owns n1 = 2w, 2w+1 ----
-      stage1_pair(sig + kSigStride * lane, s_cst + warp * kS1ConstVec, 2 * warp, zbuf + lane);
+      if (!(WFE_EXP & 8)) stage1_pair(sig + kSigStride * lane, s_cst + warp * kS1ConstVec, 2 * warp, zbuf + lane);
       __syncthreads();  // S2
     }
 
     // ---- stage 2 (compute half): warps 0..5 own (k2, k2+1) = (1,2)..(11,12); warp 6 owns k2 = 0;
-    //      warp 7 lane 0 runs the scheduler: bookkeeping of the PREVIOUS tile + descriptor of tile it+2 ----
+    //      warp 7 lane 0 runs the scheduler ----
     f2 pw[16];
-    if (!silent) {
+    if (!silent && !(WFE_EXP & 4)) {
       if (warp < 6)
         stage2_pair_compute(zbuf + lane, 2 * warp + 1, pw);
       else if (warp == 6)
         stage2_k0_compute(zbuf + lane, pw);
     }
     if (sched) {
-      // (1) one fence per tile orders last tile's relaxed operations before this tile's: ticket loads -> key loads
-      //     (acquire side), clip-max RED -> ticket RED (release side).  Nothing issued in this block is waited on.
+      // (1) the one fence of the tile: last tile's clip-max RED is ordered before this tile's ticket RED
       __threadfence();
-      if (prev2_b >= 0) red_add_u32(p.clip_ticket + prev2_b, 1u);
+      if (prev2_b >= 0) red_add_u32(&p.clip_state[prev2_b].y, 1u);
       prev2_b = prev_b;
-      // (2) fix-ups for the next tile's S1, decided from the tickets requested one tile ago
+      // (2) descriptor of tile it+2 from the geometry requested last tile; request the geometry of tile it+3
+      s_desc[it & 1] = make_desc<T>(p, idA, offA, availA);
+      idA = idB;
+      request_clip(p, idA, offA, availA);
+      // (3) fix-ups for the next tile's S1 from the clip states requested last tile
       int nfix = 0;
-      if (chk0 >= 0 && tk0 == (uint32_t)p.ntiles) {
-        const float floor_y = key2f(__ldcg(p.clip_key + chk0)) - 2.0f;
-        const int bt = s_pend_bt[ring_head];
-        const float pm = s_pend_min[ring_head];
-        ring_head = (ring_head + 1) & (kRing - 1);
-        --ring_count;
-        if (pm < floor_y) s_fix[nfix++] = FixEntry{chk0, bt - chk0 * p.ntiles, floor_y, pm == kNegInf};
-        if (chk1 >= 0 && tk1 == (uint32_t)p.ntiles) {
-          const float floor1 = key2f(__ldcg(p.clip_key + chk1)) - 2.0f;
-          const int bt1 = s_pend_bt[ring_head];
-          const float pm1 = s_pend_min[ring_head];
+      if (!(WFE_EXP & 16)) {
+        if (chk0 >= 0 && st0.y == (uint32_t)p.ntiles) {
+          const float floor_y = key2f(st0.x) - 2.0f;
+          const int bt = s_pend_bt[ring_head];
+          const float pm = s_pend_min[ring_head];
           ring_head = (ring_head + 1) & (kRing - 1);
           --ring_count;
-          if (pm1 < floor1) s_fix[nfix++] = FixEntry{chk1, bt1 - chk1 * p.ntiles, floor1, pm1 == kNegInf};
+          if (pm < floor_y) s_fix[nfix++] = FixEntry{chk0, bt - chk0 * p.ntiles, floor_y, pm == kNegInf};
+          if (chk1 >= 0 && st1.y == (uint32_t)p.ntiles) {
+            const float floor1 = key2f(st1.x) - 2.0f;
+            const int bt1 = s_pend_bt[ring_head];
+            const float pm1 = s_pend_min[ring_head];
+            ring_head = (ring_head + 1) & (kRing - 1);
+            --ring_count;
+            if (pm1 < floor1) s_fix[nfix++] = FixEntry{chk1, bt1 - chk1 * p.ntiles, floor1, pm1 == kNegInf};
+          }
         }
       }
       for (int f = nfix; f < 2; ++f) s_fix[f].tile = -1;
-      // (3) previous tile: publish its clip max, remember it in the ring
+      // (4) previous tile: publish its clip max, remember it in the ring
       if (prev_b >= 0) {
         float mx = -1.5f, mn = kNegInf;  // silent: max = (log10(1e-10)+4)/4, min marker = -inf
         if (!prev_silent) {
@@ -402,7 +437,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
             mn = fminf(mn, s_red[pp][1][w]);
           }
         }
-        red_max_u32(p.clip_key + prev_b, f2key(mx));
+        red_max_u32(&p.clip_state[prev_b].x, f2key(mx));
         // ring full: cannot happen while ntiles <= kRing unless other CTAs lag a whole clip behind; the oldest entry's
         // clip then has every tile assigned to a RUNNING CTA (ids are handed out in order) whose scheduler publishes
         // before it ever waits, so this wait terminates
@@ -412,8 +447,8 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
           const int ob = bt / p.ntiles;
           ring_head = (ring_head + 1) & (kRing - 1);
           --ring_count;
-          while (ld_acquire_u32(p.clip_ticket + ob) != (uint32_t)p.ntiles) __nanosleep(200);
-          const float fl = key2f(__ldcg(p.clip_key + ob)) - 2.0f;
+          while (ld_acquire_u32(&p.clip_state[ob].y) != (uint32_t)p.ntiles) __nanosleep(200);
+          const float fl = key2f(__ldcg(&p.clip_state[ob].x)) - 2.0f;
           if (pm < fl) {
             const FixEntry fx{ob, bt - ob * p.ntiles, fl, pm == kNegInf};
             for (int l = 0; l < 32; ++l)
@@ -428,22 +463,20 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
       prev_b = b;
       prev_tile = tile;
       prev_silent = silent;
-      // (4) request the tickets of the two oldest pending tiles; looked at one tile from now
+      // (5) request the states of the two oldest pending tiles' clips; looked at one tile from now
       chk0 = chk1 = -1;
       if (ring_count > 0) {
         chk0 = s_pend_bt[ring_head] / p.ntiles;
-        tk0 = ld_relaxed_u32(p.clip_ticket + chk0);
+        st0 = ld_relaxed_u64(p.clip_state + chk0);
       }
       if (ring_count > 1) {
         chk1 = s_pend_bt[(ring_head + 1) & (kRing - 1)] / p.ntiles;
-        tk1 = ld_relaxed_u32(p.clip_ticket + chk1);
+        st1 = ld_relaxed_u64(p.clip_state + chk1);
       }
-      // (5) descriptor of tile it+2 (slot of tile it, whose descriptor is in registers)
-      s_desc[it & 1] = make_desc<T>(p, id2);
     }
 
     if (!silent) {
-      if (warp < 7) {
+      if (warp < 7 && !(WFE_EXP & 4)) {
         bar_sync_named(1, 7 * 32);  // S2b (warps 0..6): all z planes have been read; the power buffer may overwrite them
         if (warp < 6)
           stage2_pair_store(pw, 2 * warp + 1, zbuf + lane);
@@ -451,54 +484,44 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
           stage2_k0_store(pw, zbuf + lane);
       }
       __syncthreads();  // S3
-      // ---- stage 3: banded mel projection with mma.sync TF32, epilogue log10 / scale / store ----
-      {
-        const int g = lane >> 2, t = lane & 3;
-        const int mt = (warp & 1) * 16;  // units come in (frames 0..15, frames 16..31) pairs per 8-mel tile
-        // this thread's outputs per unit: frames mt+g, mt+g+8 (columns) x mels nb+2t, nb+2t+1 (rows); a warp's units
-        // are 8 apart, i.e. 4 mel tiles = 32 rows apart: two running row pointers, no per-unit multiplies
-        float* q0 = p.out + ((size_t)b * p.n_mel + 4 * (warp >> 1) * 2 + 2 * t) * p.n_frames + t0 + mt + g;
-        const size_t row = (size_t)p.n_frames, step = 32 * row;
-        const bool full = nvalid == kTileF;
-        const int4* up = reinterpret_cast<const int4*>(s_units) + warp;
-        const float* abase = zbuf + t * kPStride + mt + g;
-        for (int u = warp; u < p.n_units; u += kWarps, up += kWarps, q0 += step) {
-          const int4 mu = *up;  // kstep0, ks, kb, nb
-          float acc[4] = {0.f, 0.f, 0.f, 0.f};
-          const float* arow = abase + mu.z * kPStride;
-          const float2* brow = s_btab + mu.x * 32 + lane;
+      // ---- stage 3: banded mel projection, exact fp32.  Half-warp h owns mel m_s + h of each of a group's four slots,
+      //      lane pr owns frames 2pr, 2pr+1.  Per table row: 2 LDS.128 (4 x (offset, weight)), 4 LDS.64 (power pairs of
+      //      the two frames), 4 FFMA2 with the weight broadcast: four independent chains per thread ----
+      if (!(WFE_EXP & 2)) {
+        const int h = lane >> 4, pr = lane & 15;
+        const bool vec_ok = nvalid == kTileF && (p.n_frames & 1) == 0;
+        const float* const pw = zbuf + 2 * pr;  // power pair (frames 2pr, 2pr+1) of bin row 0
+        float* const obase = p.out + ((size_t)b * p.n_mel + h) * p.n_frames + t0 + 2 * pr;
+        const int g_end = p.mel_wrange[warp + 1];
+        for (int gi = p.mel_wrange[warp]; gi < g_end; ++gi) {
+          const int4 gd = *reinterpret_cast<const int4*>(&s_groups[gi]);            // trips, tab_idx, valid
+          const int4 go = *(reinterpret_cast<const int4*>(&s_groups[gi]) + 1);      // out_off[0..3]
+          const int4* e = s_mtab + gd.y + 2 * h;
+          f2 a0 = mk2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
 #pragma unroll 2
-          for (int s = 0; s < mu.y; ++s) {
-            // fp32 bit patterns go in as-is: the tensor core reads the top 19 bits (truncation); the filter weights
-            // carry a (1 + 2^-11) factor that centres the truncation error (see wfe_api.cu)
-            uint32_t a[4];
-            a[0] = __float_as_uint(arow[0]);
-            a[1] = __float_as_uint(arow[8]);
-            a[2] = __float_as_uint(arow[4 * kPStride]);
-            a[3] = __float_as_uint(arow[4 * kPStride + 8]);
-            const float2 bw = *brow;
-            mma_tf32_16x8x8(acc, a, __float_as_uint(bw.x), __float_as_uint(bw.y));
-            arow += 8 * kPStride;
-            brow += 32;
+          for (int i = 0; i < gd.x; ++i, e += 4) {
+            const int4 r0 = e[0], r1 = e[1];  // slots 0,1 and 2,3: (power-row float offset, weight) x 2
+            a0 = vfma(f2{*reinterpret_cast<const float2*>(pw + r0.x)}, __int_as_float(r0.y), a0);
+            a1 = vfma(f2{*reinterpret_cast<const float2*>(pw + r0.z)}, __int_as_float(r0.w), a1);
+            a2 = vfma(f2{*reinterpret_cast<const float2*>(pw + r1.x)}, __int_as_float(r1.y), a2);
+            a3 = vfma(f2{*reinterpret_cast<const float2*>(pw + r1.z)}, __int_as_float(r1.w), a3);
           }
-          // c0: (frame mt+g, mel nb+2t)  c1: (mt+g, nb+2t+1)  c2: (mt+g+8, nb+2t)  c3: (mt+g+8, nb+2t+1)
-          const float y0 = logmel_feature(acc[0]), y1 = logmel_feature(acc[1]);
-          const float y2 = logmel_feature(acc[2]), y3 = logmel_feature(acc[3]);
-          float* q1 = q0 + row;
-          if (full && mu.w + 8 <= p.n_mel) {
-            q0[0] = y0;
-            q1[0] = y1;
-            q0[8] = y2;
-            q1[8] = y3;
-            tmax_y = fmaxf(tmax_y, fmaxf(fmaxf(y0, y1), fmaxf(y2, y3)));
-            tmin_y = fminf(tmin_y, fminf(fminf(y0, y1), fminf(y2, y3)));
-          } else {
-            const bool f0 = mt + g < nvalid, f1 = mt + g + 8 < nvalid;
-            const bool m0 = mu.w + 2 * t < p.n_mel, m1 = mu.w + 2 * t + 1 < p.n_mel;
-            if (f0 && m0) { q0[0] = y0; tmax_y = fmaxf(tmax_y, y0); tmin_y = fminf(tmin_y, y0); }
-            if (f0 && m1) { q1[0] = y1; tmax_y = fmaxf(tmax_y, y1); tmin_y = fminf(tmin_y, y1); }
-            if (f1 && m0) { q0[8] = y2; tmax_y = fmaxf(tmax_y, y2); tmin_y = fminf(tmin_y, y2); }
-            if (f1 && m1) { q1[8] = y3; tmax_y = fmaxf(tmax_y, y3); tmin_y = fminf(tmin_y, y3); }
+          const f2 acc[4] = {a0, a1, a2, a3};
+          const int off[4] = {go.x, go.y, go.z, go.w};
+#pragma unroll
+          for (int sl = 0; sl < 4; ++sl) {
+            const float y0 = logmel_feature(acc[sl].v.x), y1 = logmel_feature(acc[sl].v.y);
+            float* q0 = obase + off[sl];
+            if ((gd.z >> (2 * sl + h)) & 1) {
+              if (vec_ok) {
+                *reinterpret_cast<float2*>(q0) = make_float2(y0, y1);
+                tmax_y = fmaxf(tmax_y, fmaxf(y0, y1));
+                tmin_y = fminf(tmin_y, fminf(y0, y1));
+              } else {
+                if (2 * pr < nvalid) { q0[0] = y0; tmax_y = fmaxf(tmax_y, y0); tmin_y = fminf(tmin_y, y0); }
+                if (2 * pr + 1 < nvalid) { q0[1] = y1; tmax_y = fmaxf(tmax_y, y1); tmin_y = fminf(tmin_y, y1); }
+              }
+            }
           }
         }
       }
@@ -519,11 +542,11 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
   }
   cp_async_wait<0>();
 
-  // ---- epilogue: publish the last tile, then drain the tiles this CTA still has pending (every remaining tile of
-  //      their clips is owned by a running CTA, so the waits terminate) ----
+  // ---- epilogue: publish the last two tiles, then drain the tiles this CTA still has pending (every remaining tile
+  //      of their clips is owned by a running CTA whose scheduler publishes before it waits: the waits terminate) ----
   if (sched) {
     __threadfence();
-    if (prev2_b >= 0) red_add_u32(p.clip_ticket + prev2_b, 1u);
+    if (prev2_b >= 0) red_add_u32(&p.clip_state[prev2_b].y, 1u);
     if (prev_b >= 0) {
       float mx = -1.5f, mn = kNegInf;
       if (!prev_silent) {
@@ -536,17 +559,17 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
           mn = fminf(mn, s_red[pp][1][w]);
         }
       }
-      red_max_u32(p.clip_key + prev_b, f2key(mx));
+      red_max_u32(&p.clip_state[prev_b].x, f2key(mx));
       __threadfence();
-      red_add_u32(p.clip_ticket + prev_b, 1u);
+      red_add_u32(&p.clip_state[prev_b].y, 1u);
       if (ring_count < kRing) {
         const int slot = (ring_head + ring_count) & (kRing - 1);
         s_pend_bt[slot] = prev_b * p.ntiles + prev_tile;
         s_pend_min[slot] = mn;
         ++ring_count;
       } else {  // ring full (see above): fix this one serially once its clip completes
-        while (ld_acquire_u32(p.clip_ticket + prev_b) != (uint32_t)p.ntiles) __nanosleep(200);
-        const float fl = key2f(__ldcg(p.clip_key + prev_b)) - 2.0f;
+        while (ld_acquire_u32(&p.clip_state[prev_b].y) != (uint32_t)p.ntiles) __nanosleep(200);
+        const float fl = key2f(__ldcg(&p.clip_state[prev_b].x)) - 2.0f;
         if (mn < fl) {
           const FixEntry fx{prev_b, prev_tile, fl, mn == kNegInf};
           for (int l = 0; l < 32; ++l)
@@ -571,8 +594,8 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
         const int ob = bt / p.ntiles;
         ring_head = (ring_head + 1) & (kRing - 1);
         --ring_count;
-        while (ld_acquire_u32(p.clip_ticket + ob) != (uint32_t)p.ntiles) __nanosleep(100);
-        const float fl = key2f(__ldcg(p.clip_key + ob)) - 2.0f;
+        while (ld_acquire_u32(&p.clip_state[ob].y) != (uint32_t)p.ntiles) __nanosleep(100);
+        const float fl = key2f(__ldcg(&p.clip_state[ob].x)) - 2.0f;
         s_fix[0] = FixEntry{ob, pm < fl ? bt - ob * p.ntiles : -1, fl, pm == kNegInf};
       }
     }

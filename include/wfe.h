@@ -75,8 +75,8 @@ typedef struct wfe_config {
 
 /* mel_filters: HOST pointer, (n_fft/2+1, n_mel) row-major float32 — `fe.mel_filters.astype(float32)`,
  * the cast HF applies at use (HF:...feature_extraction_whisper.py:152).  The handle stores it in banded
- * (block-sparse, TF32) form for the tensor-pipe projection; it must be banded like every triangular mel bank
- * (<= 64 non-zero 8-mel x 8-bin blocks; the Whisper banks have 32-33). */
+ * form (per-mel lists of non-zeros, fp32); it must be sparse like every triangular mel bank: at most 1024 entries
+ * after pairing adjacent mels (the Whisper banks need about 215). */
 int wfe_create(const wfe_config* cfg, const float* mel_filters, wfe_handle** out);
 void wfe_destroy(wfe_handle* h);
 const char* wfe_last_error(void);
