@@ -75,7 +75,7 @@ struct HostSlot {
 struct wfe_handle {
   wfe_config cfg;
   int n_frames = 0, ntiles = 0, n_groups = 0, n_rows = 0, sm_count = 0;
-  int mel_wrange[wfe::kWarps + 1] = {0};
+  int mel_wrange[wfe::kMelWarps + 1] = {0};
   int ctas_per_sm[2] = {0, 0};   // resident CTAs of logmel_kernel<float>, <int16_t>
   float4* d_s1_consts = nullptr;       // [8][25]
   int4* d_mel_tab = nullptr;             // [n_rows][2][2]
@@ -112,7 +112,7 @@ int launch_logmel(wfe_handle* h, const void* pcm, float scale, const int64_t* of
   p.s1_consts = h->d_s1_consts;
   p.mel_tab = h->d_mel_tab;
   p.mel_groups = h->d_mel_groups;
-  for (int w = 0; w <= wfe::kWarps; ++w) p.mel_wrange[w] = h->mel_wrange[w];
+  for (int w = 0; w <= wfe::kMelWarps; ++w) p.mel_wrange[w] = h->mel_wrange[w];
   p.pcm_scale = scale;
   p.n_mel = h->cfg.n_mel;
   p.n_samples = h->cfg.n_samples;
@@ -218,6 +218,13 @@ int retire_slot(wfe_handle* h, HostSlot& s) {
 
 extern "C" {
 
+#if WFE_EXP & 256
+// timing-trace build only: copy the device trace buffer out (not part of the shipped ABI)
+int wfe_debug_read_trace(unsigned long long* dst, int n) {
+  return (int)cudaMemcpyFromSymbol(dst, wfe::g_trace, sizeof(unsigned long long) * n);
+}
+#endif
+
 const char* wfe_last_error(void) { return g_err.c_str(); }
 int wfe_abi_version(void) { return WFE_ABI_VERSION; }
 uint64_t wfe_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
@@ -283,18 +290,18 @@ int wfe_create(const wfe_config* cfg, const float* mel_filters, wfe_handle** out
   };
   std::vector<GroupCost> gpool;
   for (size_t i = 0; i < prs.size(); i += 4) gpool.push_back({(int)i, 14 * (prs[i].n < 1 ? 1 : prs[i].n) + 50});
-  std::vector<std::vector<int>> per_warp(wfe::kWarps);
-  int load[wfe::kWarps] = {0};
+  std::vector<std::vector<int>> per_warp(wfe::kMelWarps);
+  int load[wfe::kMelWarps] = {0};
   for (const GroupCost& gc : gpool) {  // longest-processing-time first (gpool is already sorted by cost, descending)
     int w = 0;
-    for (int i = 1; i < wfe::kWarps; ++i)
+    for (int i = 1; i < wfe::kMelWarps; ++i)
       if (load[i] < load[w]) w = i;
     per_warp[w].push_back(gc.first);
     load[w] += gc.cost;
   }
   std::vector<int4> mtab;
   std::vector<wfe::MelGroup> groups;
-  for (int w = 0; w < wfe::kWarps; ++w) {
+  for (int w = 0; w < wfe::kMelWarps; ++w) {
     h->mel_wrange[w] = (int)groups.size();
     for (int first : per_warp[w]) {
       wfe::MelGroup g;
@@ -334,7 +341,7 @@ int wfe_create(const wfe_config* cfg, const float* mel_filters, wfe_handle** out
       groups.push_back(g);
     }
   }
-  h->mel_wrange[wfe::kWarps] = (int)groups.size();
+  h->mel_wrange[wfe::kMelWarps] = (int)groups.size();
   h->n_groups = (int)groups.size();
   h->n_rows = (int)(mtab.size() / 4);
   if (h->n_groups > wfe::kMaxMelGroups || h->n_rows > wfe::kMaxMelRows) {

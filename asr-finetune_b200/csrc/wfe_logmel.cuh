@@ -34,8 +34,32 @@
 
 namespace wfe {
 
+#if WFE_EXP & 256
+// timing-trace build: lane 0 of every warp of CTAs 0..3 stamps clock64() at each stage boundary of iterations 8..15;
+// the scheduler lane additionally stamps the steps of its block (read back with wfe_debug_read_trace)
+__device__ unsigned long long g_trace[4 * 8 * 8 * 12 + 4 * 8 * 8];
+#define WFE_TRACE(pt)                                                                                        \
+  do {                                                                                                       \
+    if (lane == 0 && blockIdx.x < 4 && it >= 8 && it < 16)                                                   \
+      g_trace[((blockIdx.x * 8 + (it - 8)) * 8 + warp) * 12 + (pt)] = clock64();                             \
+  } while (0)
+#define WFE_TRACE_S(pt)                                                                                      \
+  do {                                                                                                       \
+    if (blockIdx.x < 4 && it >= 8 && it < 16)                                                                \
+      g_trace[4 * 8 * 8 * 12 + (blockIdx.x * 8 + (it - 8)) * 8 + (pt)] = clock64();                          \
+  } while (0)
+#else
+#define WFE_TRACE(pt) \
+  do {                \
+  } while (0)
+#define WFE_TRACE_S(pt) \
+  do {                  \
+  } while (0)
+#endif
+
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
+constexpr int kMelWarps = 7;  // warps 0..6 run stages 2-3; warp 7 is the scheduler / bookkeeping warp after stage 1
 constexpr int kSigLen = (kTileF - 1) * kHop + kNFft;  // 5360 padded-signal samples per tile
 constexpr int kSigStride = kHop + 2;                  // +2 pad words per 160 samples: conflict-free LDS.64 across frames
 constexpr int kSigSm = kSigLen + 2 * (kSigLen / kHop) + 4;   // 5430 floats per staging buffer (two of them)
@@ -87,7 +111,7 @@ struct LogmelParams {
   const float4* s1_consts;  // [8][25] per-warp window/twiddle block
   const int4* mel_tab;      // [n_rows][2 halves][2] : (power-row float offset, weight bits) x 4 slots per half
   const MelGroup* mel_groups;  // [n_groups], grouped by warp
-  int mel_wrange[kWarps + 1];  // warp w owns groups [mel_wrange[w], mel_wrange[w+1])
+  int mel_wrange[kMelWarps + 1];  // warp w < kMelWarps owns groups [mel_wrange[w], mel_wrange[w+1])
   float pcm_scale;
   int n_mel, n_samples, n_frames, ntiles, n_groups, n_rows;
   uint32_t total_tiles;
@@ -297,7 +321,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
   __shared__ float s_red[2][2][kWarps];  // [tile parity][max, min][warp]
   __shared__ TileDesc s_desc[2];         // descriptor of tile k lives in slot k & 1
   __shared__ FixEntry s_fix[2];
-  __shared__ int s_pend_bt[kRing];       // clip * ntiles + tile
+  __shared__ int2 s_pend_bt[kRing];      // (clip, tile)
   __shared__ float s_pend_min[kRing];    // tile minimum of y; -inf marks a silent (not yet written) tile
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -349,6 +373,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
     const bool silent = cur.mode == kModeSilent;
     float* const sig = sigbuf + (it & 1) * kSigBuf;
 
+    WFE_TRACE(0);
     // ---- top: start the NEXT tile's loads, then make sure this tile's signal has landed ----
     uint32_t idB = 0;
     if (sched) idB = atomicAdd(p.tile_counter, 1u);  // id of tile it+3, first used in this tile's stage 2
@@ -367,7 +392,9 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
     }
     if (p.mask != nullptr && tid < nvalid) p.mask[(size_t)b * p.n_frames + t0 + tid] = ((t0 + tid) * kHop < len) ? 1 : 0;
     cp_async_wait<1>();  // everything but the group just committed (= this tile's signal) is complete
+    WFE_TRACE(1);
     __syncthreads();     // S1: signal visible to all warps; s_fix / s_desc from the previous stage 2 published
+    WFE_TRACE(2);
 
     // ---- clamp fix-ups decided during the previous tile (own tiles, L2-resident) ----
     if (!(WFE_EXP & 1)) {
@@ -381,8 +408,11 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
     float tmax_y = -1.5f, tmin_y = 3.0e38f;
     if (!silent) {
       // ---- stage 1: warp w owns n1 = 2w, 2w+1 ----
+      WFE_TRACE(3);
       if (!(WFE_EXP & 8)) stage1_pair(sig + kSigStride * lane, s_cst + warp * kS1ConstVec, 2 * warp, zbuf + lane);
+      WFE_TRACE(4);
       __syncthreads();  // S2
+      WFE_TRACE(5);
     }
 
     // ---- stage 2 (compute half): warps 0..5 own (k2, k2+1) = (1,2)..(11,12); warp 6 owns k2 = 0;
@@ -396,34 +426,39 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
     }
     if (sched) {
       // (1) the one fence of the tile: last tile's clip-max RED is ordered before this tile's ticket RED
+      WFE_TRACE_S(0);
       __threadfence();
+      WFE_TRACE_S(1);
       if (prev2_b >= 0) red_add_u32(&p.clip_state[prev2_b].y, 1u);
       prev2_b = prev_b;
       // (2) descriptor of tile it+2 from the geometry requested last tile; request the geometry of tile it+3
       s_desc[it & 1] = make_desc<T>(p, idA, offA, availA);
+      WFE_TRACE_S(2);
       idA = idB;
       request_clip(p, idA, offA, availA);
+      WFE_TRACE_S(3);
       // (3) fix-ups for the next tile's S1 from the clip states requested last tile
       int nfix = 0;
       if (!(WFE_EXP & 16)) {
         if (chk0 >= 0 && st0.y == (uint32_t)p.ntiles) {
           const float floor_y = key2f(st0.x) - 2.0f;
-          const int bt = s_pend_bt[ring_head];
+          const int2 bt = s_pend_bt[ring_head];
           const float pm = s_pend_min[ring_head];
           ring_head = (ring_head + 1) & (kRing - 1);
           --ring_count;
-          if (pm < floor_y) s_fix[nfix++] = FixEntry{chk0, bt - chk0 * p.ntiles, floor_y, pm == kNegInf};
+          if (pm < floor_y) s_fix[nfix++] = FixEntry{bt.x, bt.y, floor_y, pm == kNegInf};
           if (chk1 >= 0 && st1.y == (uint32_t)p.ntiles) {
             const float floor1 = key2f(st1.x) - 2.0f;
-            const int bt1 = s_pend_bt[ring_head];
+            const int2 bt1 = s_pend_bt[ring_head];
             const float pm1 = s_pend_min[ring_head];
             ring_head = (ring_head + 1) & (kRing - 1);
             --ring_count;
-            if (pm1 < floor1) s_fix[nfix++] = FixEntry{chk1, bt1 - chk1 * p.ntiles, floor1, pm1 == kNegInf};
+            if (pm1 < floor1) s_fix[nfix++] = FixEntry{bt1.x, bt1.y, floor1, pm1 == kNegInf};
           }
         }
       }
       for (int f = nfix; f < 2; ++f) s_fix[f].tile = -1;
+      WFE_TRACE_S(4);
       // (4) previous tile: publish its clip max, remember it in the ring
       if (prev_b >= 0) {
         float mx = -1.5f, mn = kNegInf;  // silent: max = (log10(1e-10)+4)/4, min marker = -inf
@@ -432,7 +467,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
           mx = s_red[pp][0][0];
           mn = s_red[pp][1][0];
 #pragma unroll
-          for (int w = 1; w < kWarps; ++w) {
+          for (int w = 1; w < kMelWarps; ++w) {
             mx = fmaxf(mx, s_red[pp][0][w]);
             mn = fminf(mn, s_red[pp][1][w]);
           }
@@ -442,48 +477,54 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
         // clip then has every tile assigned to a RUNNING CTA (ids are handed out in order) whose scheduler publishes
         // before it ever waits, so this wait terminates
         if (ring_count == kRing) {
-          const int bt = s_pend_bt[ring_head];
+          const int2 bt = s_pend_bt[ring_head];
           const float pm = s_pend_min[ring_head];
-          const int ob = bt / p.ntiles;
+          const int ob = bt.x;
           ring_head = (ring_head + 1) & (kRing - 1);
           --ring_count;
           while (ld_acquire_u32(&p.clip_state[ob].y) != (uint32_t)p.ntiles) __nanosleep(200);
           const float fl = key2f(__ldcg(&p.clip_state[ob].x)) - 2.0f;
           if (pm < fl) {
-            const FixEntry fx{ob, bt - ob * p.ntiles, fl, pm == kNegInf};
+            const FixEntry fx{ob, bt.y, fl, pm == kNegInf};
             for (int l = 0; l < 32; ++l)
               for (int w = 0; w < kWarps; ++w) fix_tile(p.out, p.n_mel, p.n_frames, fx, w, l);
           }
         }
         const int slot = (ring_head + ring_count) & (kRing - 1);
-        s_pend_bt[slot] = prev_b * p.ntiles + prev_tile;
+        s_pend_bt[slot] = make_int2(prev_b, prev_tile);
         s_pend_min[slot] = mn;
         ++ring_count;
       }
       prev_b = b;
       prev_tile = tile;
       prev_silent = silent;
+      WFE_TRACE_S(5);
       // (5) request the states of the two oldest pending tiles' clips; looked at one tile from now
       chk0 = chk1 = -1;
       if (ring_count > 0) {
-        chk0 = s_pend_bt[ring_head] / p.ntiles;
+        chk0 = s_pend_bt[ring_head].x;
         st0 = ld_relaxed_u64(p.clip_state + chk0);
       }
       if (ring_count > 1) {
-        chk1 = s_pend_bt[(ring_head + 1) & (kRing - 1)] / p.ntiles;
+        chk1 = s_pend_bt[(ring_head + 1) & (kRing - 1)].x;
         st1 = ld_relaxed_u64(p.clip_state + chk1);
       }
+      WFE_TRACE_S(6);
     }
 
-    if (!silent) {
-      if (warp < 7 && !(WFE_EXP & 4)) {
-        bar_sync_named(1, 7 * 32);  // S2b (warps 0..6): all z planes have been read; the power buffer may overwrite them
+    WFE_TRACE(6);
+    if (!silent && warp < kMelWarps) {
+      if (!(WFE_EXP & 4)) {
+        bar_sync_named(1, kMelWarps * 32);  // S2b (warps 0..6): all z planes have been read; the power may overwrite them
         if (warp < 6)
           stage2_pair_store(pw, 2 * warp + 1, zbuf + lane);
         else
           stage2_k0_store(pw, zbuf + lane);
       }
-      __syncthreads();  // S3
+      WFE_TRACE(7);
+      bar_sync_named(2, kMelWarps * 32);  // S3 (warps 0..6): power buffer complete.  Warp 7 only rejoins at S4, so its
+                                          // scheduler block overlaps stages 2 and 3
+      WFE_TRACE(8);
       // ---- stage 3: banded mel projection, exact fp32.  Half-warp h owns mel m_s + h of each of a group's four slots,
       //      lane pr owns frames 2pr, 2pr+1.  Per table row: 2 LDS.128 (4 x (offset, weight)), 4 LDS.64 (power pairs of
       //      the two frames), 4 FFMA2 with the weight broadcast: four independent chains per thread ----
@@ -535,7 +576,9 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
         s_red[it & 1][1][warp] = tmin_y;
       }
     }
+    WFE_TRACE(9);
     __syncthreads();  // S4: tile written (visible to this CTA); s_desc / s_fix / s_red published; smem free
+    WFE_TRACE(10);
     cur = nxt;
     nxt = s_desc[it & 1];
     ++it;
@@ -554,7 +597,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
         mx = s_red[pp][0][0];
         mn = s_red[pp][1][0];
 #pragma unroll
-        for (int w = 1; w < kWarps; ++w) {
+        for (int w = 1; w < kMelWarps; ++w) {
           mx = fmaxf(mx, s_red[pp][0][w]);
           mn = fminf(mn, s_red[pp][1][w]);
         }
@@ -564,7 +607,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
       red_add_u32(&p.clip_state[prev_b].y, 1u);
       if (ring_count < kRing) {
         const int slot = (ring_head + ring_count) & (kRing - 1);
-        s_pend_bt[slot] = prev_b * p.ntiles + prev_tile;
+        s_pend_bt[slot] = make_int2(prev_b, prev_tile);
         s_pend_min[slot] = mn;
         ++ring_count;
       } else {  // ring full (see above): fix this one serially once its clip completes
@@ -589,14 +632,14 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
     if (sched) {
       s_fix[0].tile = -2;  // -2: ring empty
       if (ring_count > 0) {
-        const int bt = s_pend_bt[ring_head];
+        const int2 bt = s_pend_bt[ring_head];
         const float pm = s_pend_min[ring_head];
-        const int ob = bt / p.ntiles;
+        const int ob = bt.x;
         ring_head = (ring_head + 1) & (kRing - 1);
         --ring_count;
         while (ld_acquire_u32(&p.clip_state[ob].y) != (uint32_t)p.ntiles) __nanosleep(100);
         const float fl = key2f(__ldcg(&p.clip_state[ob].x)) - 2.0f;
-        s_fix[0] = FixEntry{ob, pm < fl ? bt - ob * p.ntiles : -1, fl, pm == kNegInf};
+        s_fix[0] = FixEntry{ob, pm < fl ? bt.y : -1, fl, pm == kNegInf};
       }
     }
     __syncthreads();
