@@ -88,9 +88,9 @@ struct wfe_handle {
 
 namespace {
 
-size_t scratch_bytes(const wfe_handle*, int batch) {
-  // clip_state[B] = {max key, ticket} (8 B each), tile_counter (+ pad to 16 B)
-  return ((size_t)batch * 2 + 4) * sizeof(uint32_t);
+size_t scratch_bytes(const wfe_handle* h, int batch) {
+  // tile_key[B][ntiles] (one word per tile, zero = not published yet), tile_counter (+ pad to 16 B)
+  return ((size_t)batch * h->ntiles + 4) * sizeof(uint32_t);
 }
 
 template <typename T>
@@ -106,9 +106,9 @@ int launch_logmel(wfe_handle* h, const void* pcm, float scale, const int64_t* of
   p.norm = reinterpret_cast<const float2*>(norm);
   p.out = out;
   p.mask = mask;
-  if ((reinterpret_cast<uintptr_t>(scratch) & 7u) != 0) return fail(WFE_ERR_INVALID, "scratch must be 8-byte aligned");
-  p.clip_state = reinterpret_cast<uint2*>(scratch);
-  p.tile_counter = reinterpret_cast<uint32_t*>(scratch) + 2 * (size_t)batch;
+  if ((reinterpret_cast<uintptr_t>(scratch) & 3u) != 0) return fail(WFE_ERR_INVALID, "scratch must be 4-byte aligned");
+  p.tile_key = reinterpret_cast<uint32_t*>(scratch);
+  p.tile_counter = p.tile_key + (size_t)batch * h->ntiles;
   p.s1_consts = h->d_s1_consts;
   p.mel_tab = h->d_mel_tab;
   p.mel_groups = h->d_mel_groups;

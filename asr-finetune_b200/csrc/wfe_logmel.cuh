@@ -14,9 +14,12 @@
 //            LDS.64 (power of two adjacent frames) + one FFMA2 with the weight broadcast covers two frames of a
 //            non-zero; epilogue log10, (x+4)/4, full-line 64-bit stores, tile min/max            (steps 8, 9, 11)
 //            (legacy mma.sync TF32 was tried and measured at CUDA-core rate on B200 - see DESIGN.md)
-//   clamp    per-clip max-8 clamp (step 10) without a second pass over HBM: every CTA remembers its own tiles and,
-//            once the clip's ticket shows all of its tiles are done, re-reads only the tiles whose minimum is below
-//            the floor from L2 and fixes them; tiles that lie entirely in the zero padding are written once, late.
+//   clamp    per-clip max-8 clamp (step 10) without a second pass over HBM and without fences or atomics: every tile
+//            stores its own maximum into a zero-initialised word tile_key[clip][tile]; a clip is complete exactly when
+//            none of its words is zero, and its maximum is the maximum of the words (each is written once, so no
+//            ordering between locations is needed).  Every CTA remembers its own tiles and, once their clip is
+//            complete, re-reads from L2 only those whose minimum is below the floor and fixes them; tiles that lie
+//            entirely in the zero padding are written once, late, as a constant.
 //
 // Arithmetic restated from HF:models/whisper/feature_extraction_whisper.py:135-164;
 // 400 = 16 x 25 Cooley-Tukey: n = n1 + 16*n2, k = k2 + 25*k1,
@@ -105,8 +108,8 @@ struct LogmelParams {
   const float2* norm;       // (mean, rstd) per clip or nullptr
   float* out;               // (B, n_mel, n_frames)
   int32_t* mask;            // (B, n_frames) or nullptr
-  uint2* clip_state;        // [B] {x: running max of y = (log10(mel)+4)/4 as ordered key, y: finished-tile ticket};
-                            //     one 8-byte word so that a single 64-bit load sees a consistent pair (zero-init)
+  uint32_t* tile_key;       // [B][ntiles] max of y = (log10(mel)+4)/4 over the tile as an ordered key; 0 = not yet
+                            //     published (zero-initialised; keys of finite floats are never 0)
   uint32_t* tile_counter;   // [1] dynamic tile scheduler (zero-initialised)
   const float4* s1_consts;  // [8][25] per-warp window/twiddle block
   const int4* mel_tab;      // [n_rows][2 halves][2] : (power-row float offset, weight bits) x 4 slots per half
@@ -143,28 +146,13 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-// {key, ticket} of a clip in ONE 64-bit access: if the ticket it returns is complete, the key it returns is final
-// (every writer's max is performed before its ticket increment, and this load is performed at a single instant)
-__device__ __forceinline__ uint2 ld_relaxed_u64(const uint2* p) {
-  uint2 v;
-  asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void red_max_u32(uint32_t* p, uint32_t v) {
-  asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ void red_add_u32(uint32_t* p, uint32_t v) {
-  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
   uint32_t v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 // named barrier over the first `nthreads` threads' warps (id 1..15; 0 is __syncthreads)
 __device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
@@ -310,6 +298,23 @@ __device__ __forceinline__ void prefetch_signal(float* __restrict__ sig, const f
   if (r0 == 0 && c < (kSigLen - kRows * kHop) / 2) cp_async8(d + kRows * kSigStride, g + kRows * kHop);
 }
 
+// block (whole warp) until every tile of clip `b` has published its maximum; returns the clamp floor max - 2
+__device__ __forceinline__ float wait_clip_floor(const LogmelParams& p, int b, int lane) {
+  const uint32_t* row = p.tile_key + (size_t)b * p.ntiles;
+  for (;;) {
+    uint32_t m = 1u;
+    bool zero = false;
+    for (int w = lane; w < p.ntiles; w += 32) {
+      const uint32_t k = ld_relaxed_u32(row + w);
+      zero |= k == 0;
+      m = max(m, k);
+    }
+    m = __reduce_max_sync(0xffffffffu, m);
+    if (!__any_sync(0xffffffffu, zero)) return key2f(m) - 2.0f;
+    __nanosleep(200);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams p) {
   extern __shared__ __align__(16) float smem[];
@@ -326,19 +331,13 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float kNegInf = -__int_as_float(0x7f800000);
-  const bool sched = tid == 7 * 32;  // lane 0 of warp 7 (idle in stage 2): tile scheduler + clip bookkeeping
+  const bool sched = tid == 7 * 32;  // lane 0 of warp 7: tile scheduler; the whole of warp 7 keeps the clamp's books
 
-  // scheduler-lane state.  Everything it needs from global memory is REQUESTED in one tile and CONSUMED in the next,
-  // so the lane never waits on a load; the only fence it executes finds nothing outstanding.
-  //   idA: id of tile it+2, its clip geometry (offA, availA) requested last tile -> descriptor written this tile
-  //   stA/stB: {key, ticket} of the two oldest pending tiles' clips, requested last tile
-  //   prev: the previous tile (clip max published this tile); prev2: the one before (ticket published this tile)
+  // warp-7 state (uniform across its lanes): ring of this CTA's pending tiles and the previous tile, whose maximum is
+  // published one tile late.  Everything the block needs from global memory is requested at its start and consumed
+  // at its end; it executes no fence and no atomic besides the tile-counter increment.
   int ring_head = 0, ring_count = 0;
-  int prev_b = -1, prev_tile = 0, prev_silent = 0, prev2_b = -1;
-  int chk0 = -1, chk1 = -1;
-  uint2 st0 = make_uint2(0, 0), st1 = make_uint2(0, 0);
-  uint32_t idA = 0;
-  int64_t offA = 0, availA = 0;
+  int prev_b = -1, prev_tile = 0, prev_silent = 0;
 
   // ---- one-time CTA set-up ----
   for (int i = tid; i < 8 * kS1ConstVec; i += kThreads) s_cst[i] = p.s1_consts[i];
@@ -347,13 +346,11 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
   if (sched) {
     const uint32_t id0 = atomicAdd(p.tile_counter, 1u);
     const uint32_t id1 = atomicAdd(p.tile_counter, 1u);
-    idA = atomicAdd(p.tile_counter, 1u);
     int64_t o, a;
     request_clip(p, id0, o, a);
     s_desc[0] = make_desc<T>(p, id0, o, a);
     request_clip(p, id1, o, a);
     s_desc[1] = make_desc<T>(p, id1, o, a);
-    request_clip(p, idA, offA, availA);
     s_fix[0].tile = -1;
     s_fix[1].tile = -1;
   }
@@ -376,7 +373,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
     WFE_TRACE(0);
     // ---- top: start the NEXT tile's loads, then make sure this tile's signal has landed ----
     uint32_t idB = 0;
-    if (sched) idB = atomicAdd(p.tile_counter, 1u);  // id of tile it+3, first used in this tile's stage 2
+    if (sched) idB = atomicAdd(p.tile_counter, 1u);  // id of tile it+2, first used in this tile's stage 2
     if (nxt.b >= 0 && nxt.mode == kModeAsync)
       prefetch_signal(sigbuf + ((it + 1) & 1) * kSigBuf,
                       reinterpret_cast<const float*>(p.pcm) + nxt.off + nxt.tile * kTileF * kHop - kNFft / 2, tid);
@@ -424,91 +421,101 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
       else if (warp == 6)
         stage2_k0_compute(zbuf + lane, pw);
     }
-    if (sched) {
-      // (1) the one fence of the tile: last tile's clip-max RED is ordered before this tile's ticket RED
+    if (warp == 7) {
+      // ---- warp 7: tile scheduler + clamp bookkeeping, overlapping stages 2 and 3 of warps 0..6 ----
       WFE_TRACE_S(0);
-      __threadfence();
-      WFE_TRACE_S(1);
-      if (prev2_b >= 0) red_add_u32(&p.clip_state[prev2_b].y, 1u);
-      prev2_b = prev_b;
-      // (2) descriptor of tile it+2 from the geometry requested last tile; request the geometry of tile it+3
-      s_desc[it & 1] = make_desc<T>(p, idA, offA, availA);
-      WFE_TRACE_S(2);
-      idA = idB;
-      request_clip(p, idA, offA, availA);
-      WFE_TRACE_S(3);
-      // (3) fix-ups for the next tile's S1 from the clip states requested last tile
-      int nfix = 0;
-      if (!(WFE_EXP & 16)) {
-        if (chk0 >= 0 && st0.y == (uint32_t)p.ntiles) {
-          const float floor_y = key2f(st0.x) - 2.0f;
-          const int2 bt = s_pend_bt[ring_head];
-          const float pm = s_pend_min[ring_head];
-          ring_head = (ring_head + 1) & (kRing - 1);
-          --ring_count;
-          if (pm < floor_y) s_fix[nfix++] = FixEntry{bt.x, bt.y, floor_y, pm == kNegInf};
-          if (chk1 >= 0 && st1.y == (uint32_t)p.ntiles) {
-            const float floor1 = key2f(st1.x) - 2.0f;
-            const int2 bt1 = s_pend_bt[ring_head];
-            const float pm1 = s_pend_min[ring_head];
-            ring_head = (ring_head + 1) & (kRing - 1);
-            --ring_count;
-            if (pm1 < floor1) s_fix[nfix++] = FixEntry{bt1.x, bt1.y, floor1, pm1 == kNegInf};
-          }
-        }
-      }
-      for (int f = nfix; f < 2; ++f) s_fix[f].tile = -1;
-      WFE_TRACE_S(4);
-      // (4) previous tile: publish its clip max, remember it in the ring
-      if (prev_b >= 0) {
-        float mx = -1.5f, mn = kNegInf;  // silent: max = (log10(1e-10)+4)/4, min marker = -inf
-        if (!prev_silent) {
-          const int pp = (it + 1) & 1;
-          mx = s_red[pp][0][0];
-          mn = s_red[pp][1][0];
+      // (1) requests first: geometry of tile it+2's clip (lane 0), and the tile_key words of the clips of the two oldest
+      //     pending tiles (lane l reads words l, l+32, l+64, l+96); all consumed at the end of the block
+      int64_t g_off = 0, g_avail = 0;
+      if (lane == 0) request_clip(p, idB, g_off, g_avail);
+      const int chk0 = ring_count > 0 ? s_pend_bt[ring_head].x : -1;
+      const int chk1 = ring_count > 1 ? s_pend_bt[(ring_head + 1) & (kRing - 1)].x : -1;
+      uint32_t k0[4], k1[4];
 #pragma unroll
-          for (int w = 1; w < kMelWarps; ++w) {
-            mx = fmaxf(mx, s_red[pp][0][w]);
-            mn = fminf(mn, s_red[pp][1][w]);
-          }
+      for (int j = 0; j < 4; ++j) {
+        const int w = lane + 32 * j;
+        k0[j] = (chk0 >= 0 && w < p.ntiles) ? ld_relaxed_u32(p.tile_key + (size_t)chk0 * p.ntiles + w) : 1u;
+        k1[j] = (chk1 >= 0 && w < p.ntiles) ? ld_relaxed_u32(p.tile_key + (size_t)chk1 * p.ntiles + w) : 1u;
+      }
+      WFE_TRACE_S(1);
+      // (2) previous tile: max / min over the 7 mel warps (three shuffles), publish the max, remember the tile
+      if (prev_b >= 0) {
+        const int pp = (it + 1) & 1;
+        float mx = lane < kMelWarps ? s_red[pp][0][lane] : -3.0e38f;
+        float mn = lane < kMelWarps ? s_red[pp][1][lane] : 3.0e38f;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+          mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
         }
-        red_max_u32(&p.clip_state[prev_b].x, f2key(mx));
+        if (prev_silent) {  // max = (log10(1e-10)+4)/4, min marker = -inf
+          mx = -1.5f;
+          mn = kNegInf;
+        }
         // ring full: cannot happen while ntiles <= kRing unless other CTAs lag a whole clip behind; the oldest entry's
-        // clip then has every tile assigned to a RUNNING CTA (ids are handed out in order) whose scheduler publishes
-        // before it ever waits, so this wait terminates
+        // clip then has every tile assigned to a RUNNING CTA (ids are handed out in order) whose warp 7 publishes
+        // without ever waiting, so this wait terminates
         if (ring_count == kRing) {
           const int2 bt = s_pend_bt[ring_head];
           const float pm = s_pend_min[ring_head];
-          const int ob = bt.x;
           ring_head = (ring_head + 1) & (kRing - 1);
           --ring_count;
-          while (ld_acquire_u32(&p.clip_state[ob].y) != (uint32_t)p.ntiles) __nanosleep(200);
-          const float fl = key2f(__ldcg(&p.clip_state[ob].x)) - 2.0f;
+          const float fl = wait_clip_floor(p, bt.x, lane);
           if (pm < fl) {
-            const FixEntry fx{ob, bt.y, fl, pm == kNegInf};
-            for (int l = 0; l < 32; ++l)
-              for (int w = 0; w < kWarps; ++w) fix_tile(p.out, p.n_mel, p.n_frames, fx, w, l);
+            const FixEntry fx{bt.x, bt.y, fl, pm == kNegInf};
+            for (int w = 0; w < kWarps; ++w) fix_tile(p.out, p.n_mel, p.n_frames, fx, w, lane);
           }
         }
-        const int slot = (ring_head + ring_count) & (kRing - 1);
-        s_pend_bt[slot] = make_int2(prev_b, prev_tile);
-        s_pend_min[slot] = mn;
+        if (lane == 0) {
+          st_relaxed_u32(p.tile_key + (size_t)prev_b * p.ntiles + prev_tile, f2key(mx));
+          const int slot = (ring_head + ring_count) & (kRing - 1);
+          s_pend_bt[slot] = make_int2(prev_b, prev_tile);
+          s_pend_min[slot] = mn;
+        }
         ++ring_count;
       }
       prev_b = b;
       prev_tile = tile;
       prev_silent = silent;
+      WFE_TRACE_S(2);
+      // (3) consume the words: a clip is complete when none of them is zero; its max is the max of the words
+      int nfix = 0;
+      if (!(WFE_EXP & 16)) {
+        const uint32_t m0 = __reduce_max_sync(0xffffffffu, max(max(k0[0], k0[1]), max(k0[2], k0[3])));
+        const bool z0 = __any_sync(0xffffffffu, (k0[0] == 0) | (k0[1] == 0) | (k0[2] == 0) | (k0[3] == 0));
+        const uint32_t m1 = __reduce_max_sync(0xffffffffu, max(max(k1[0], k1[1]), max(k1[2], k1[3])));
+        const bool z1 = __any_sync(0xffffffffu, (k1[0] == 0) | (k1[1] == 0) | (k1[2] == 0) | (k1[3] == 0));
+        if (chk0 >= 0 && !z0) {
+          const float floor_y = key2f(m0) - 2.0f;
+          const int2 bt = s_pend_bt[ring_head];
+          const float pm = s_pend_min[ring_head];
+          ring_head = (ring_head + 1) & (kRing - 1);
+          --ring_count;
+          if (pm < floor_y) {
+            if (lane == 0) s_fix[nfix] = FixEntry{bt.x, bt.y, floor_y, pm == kNegInf};
+            ++nfix;
+          }
+          if (chk1 >= 0 && !z1) {
+            const float floor1 = key2f(m1) - 2.0f;
+            const int2 bt1 = s_pend_bt[ring_head];
+            const float pm1 = s_pend_min[ring_head];
+            ring_head = (ring_head + 1) & (kRing - 1);
+            --ring_count;
+            if (pm1 < floor1) {
+              if (lane == 0) s_fix[nfix] = FixEntry{bt1.x, bt1.y, floor1, pm1 == kNegInf};
+              ++nfix;
+            }
+          }
+        }
+      }
+      if (lane == 0) {
+        for (int f = nfix; f < 2; ++f) s_fix[f].tile = -1;
+        // (4) hand tile it+2 to the CTA (slot of tile it, whose descriptor already sits in registers)
+        s_desc[it & 1] = make_desc<T>(p, idB, g_off, g_avail);
+      }
+      WFE_TRACE_S(3);
+      WFE_TRACE_S(4);
       WFE_TRACE_S(5);
-      // (5) request the states of the two oldest pending tiles' clips; looked at one tile from now
-      chk0 = chk1 = -1;
-      if (ring_count > 0) {
-        chk0 = s_pend_bt[ring_head].x;
-        st0 = ld_relaxed_u64(p.clip_state + chk0);
-      }
-      if (ring_count > 1) {
-        chk1 = s_pend_bt[(ring_head + 1) & (kRing - 1)].x;
-        st1 = ld_relaxed_u64(p.clip_state + chk1);
-      }
       WFE_TRACE_S(6);
     }
 
@@ -585,39 +592,34 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
   }
   cp_async_wait<0>();
 
-  // ---- epilogue: publish the last two tiles, then drain the tiles this CTA still has pending (every remaining tile
-  //      of their clips is owned by a running CTA whose scheduler publishes before it waits: the waits terminate) ----
-  if (sched) {
-    __threadfence();
-    if (prev2_b >= 0) red_add_u32(&p.clip_state[prev2_b].y, 1u);
-    if (prev_b >= 0) {
-      float mx = -1.5f, mn = kNegInf;
-      if (!prev_silent) {
-        const int pp = (it + 1) & 1;
-        mx = s_red[pp][0][0];
-        mn = s_red[pp][1][0];
+  // ---- epilogue: publish the last tile, then drain the tiles this CTA still has pending (every remaining tile of their
+  //      clips is owned by a running CTA whose warp 7 publishes without ever waiting: the waits terminate) ----
+  if (warp == 7 && prev_b >= 0) {
+    const int pp = (it + 1) & 1;
+    float mx = lane < kMelWarps ? s_red[pp][0][lane] : -3.0e38f;
+    float mn = lane < kMelWarps ? s_red[pp][1][lane] : 3.0e38f;
 #pragma unroll
-        for (int w = 1; w < kMelWarps; ++w) {
-          mx = fmaxf(mx, s_red[pp][0][w]);
-          mn = fminf(mn, s_red[pp][1][w]);
-        }
-      }
-      red_max_u32(&p.clip_state[prev_b].x, f2key(mx));
-      __threadfence();
-      red_add_u32(&p.clip_state[prev_b].y, 1u);
-      if (ring_count < kRing) {
+    for (int o = 4; o > 0; o >>= 1) {
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    }
+    if (prev_silent) {
+      mx = -1.5f;
+      mn = kNegInf;
+    }
+    if (lane == 0) st_relaxed_u32(p.tile_key + (size_t)prev_b * p.ntiles + prev_tile, f2key(mx));
+    if (ring_count < kRing) {
+      if (lane == 0) {
         const int slot = (ring_head + ring_count) & (kRing - 1);
         s_pend_bt[slot] = make_int2(prev_b, prev_tile);
         s_pend_min[slot] = mn;
-        ++ring_count;
-      } else {  // ring full (see above): fix this one serially once its clip completes
-        while (ld_acquire_u32(&p.clip_state[prev_b].y) != (uint32_t)p.ntiles) __nanosleep(200);
-        const float fl = key2f(__ldcg(&p.clip_state[prev_b].x)) - 2.0f;
-        if (mn < fl) {
-          const FixEntry fx{prev_b, prev_tile, fl, mn == kNegInf};
-          for (int l = 0; l < 32; ++l)
-            for (int w = 0; w < kWarps; ++w) fix_tile(p.out, p.n_mel, p.n_frames, fx, w, l);
-        }
+      }
+      ++ring_count;
+    } else {  // ring full (see above): fix this one with warp 7 alone once its clip completes
+      const float fl = wait_clip_floor(p, prev_b, lane);
+      if (mn < fl) {
+        const FixEntry fx{prev_b, prev_tile, fl, mn == kNegInf};
+        for (int w = 0; w < kWarps; ++w) fix_tile(p.out, p.n_mel, p.n_frames, fx, w, lane);
       }
     }
   }
@@ -629,17 +631,17 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
   }
   __syncthreads();
   for (;;) {
-    if (sched) {
-      s_fix[0].tile = -2;  // -2: ring empty
+    if (warp == 7) {
+      __syncwarp();  // the ring entries written by lane 0 are visible to the warp
       if (ring_count > 0) {
         const int2 bt = s_pend_bt[ring_head];
         const float pm = s_pend_min[ring_head];
-        const int ob = bt.x;
         ring_head = (ring_head + 1) & (kRing - 1);
         --ring_count;
-        while (ld_acquire_u32(&p.clip_state[ob].y) != (uint32_t)p.ntiles) __nanosleep(100);
-        const float fl = key2f(__ldcg(&p.clip_state[ob].x)) - 2.0f;
-        s_fix[0] = FixEntry{ob, pm < fl ? bt.y : -1, fl, pm == kNegInf};
+        const float fl = wait_clip_floor(p, bt.x, lane);
+        if (lane == 0) s_fix[0] = FixEntry{bt.x, pm < fl ? bt.y : -1, fl, pm == kNegInf};
+      } else if (lane == 0) {
+        s_fix[0].tile = -2;  // -2: ring empty
       }
     }
     __syncthreads();

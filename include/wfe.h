@@ -87,7 +87,7 @@ uint64_t wfe_launch_count(void);
 
 /* ---- log-mel features, device-resident input ---------------------------------------------------- */
 
-/* Bytes of device scratch wfe_logmel needs for `batch` clips (per-clip max + ticket, tile scheduler counter). */
+/* Bytes of device scratch wfe_logmel needs for `batch` clips (one max word per 32-frame tile, tile scheduler counter). */
 size_t wfe_logmel_scratch_bytes(const wfe_handle* h, int32_t batch);
 int32_t wfe_n_frames(const wfe_handle* h); /* n_samples / hop_length (3000) */
 
