@@ -14,6 +14,7 @@ ref:finetune/training/trainers/utils.py:97-112); pass `device="cpu"` for host te
 from __future__ import annotations
 
 import ctypes as C
+import itertools
 from dataclasses import dataclass, field
 from typing import Any, Callable, Iterable, Optional, Sequence
 
@@ -52,12 +53,16 @@ def _pack_ids(label_lists: Sequence[Sequence[int]]):
     buf = torch.empty(total + len(offs), dtype=torch.int64, pin_memory=True)
     flat = buf.numpy()
     flat[:len(offs)] = offs
-    pos = len(offs)
-    for ids in label_lists:
-        n = len(ids)
-        if n:
-            flat[pos:pos + n] = np.asarray(ids, dtype=np.int64) if not torch.is_tensor(ids) else ids.cpu().numpy()
-        pos += n
+    if total:
+        if all(isinstance(x, list) for x in label_lists):  # the common case: one pass over all ids
+            flat[len(offs):] = np.fromiter(itertools.chain.from_iterable(label_lists), dtype=np.int64, count=total)
+        else:
+            pos = len(offs)
+            for ids in label_lists:
+                n = len(ids)
+                if n:
+                    flat[pos:pos + n] = ids.cpu().numpy() if torch.is_tensor(ids) else np.asarray(ids, dtype=np.int64)
+                pos += n
     return buf, lens
 
 

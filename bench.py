@@ -415,11 +415,12 @@ def run_b200(args):
     e2e_steps = args.e2e_steps or min(args.steps, 5)
 
     def host_step():
+        # label half of the padding collator (H2D ids, kernel; no host sync as the labels carry no BOS to strip) is
+        # queued first so that it overlaps the blocking extractor call; its D2H read closes the step
+        lab_d = pkg.collator.collate_labels_and_features(fe, labels, None, width=None, decoder_start_token_id=-1,
+                                                         strip_bos=False)[1]
         out = fe(host_clips, sampling_rate=16000, return_tensors="pt")  # host numpy in -> host (pinned) tensors out
-        # label half of the padding collator (features are already one host batch tensor): H2D ids, kernel, D2H labels
-        lab = pkg.collator.collate_labels_and_features(fe, labels, None, width=None, decoder_start_token_id=50258,
-                                                       strip_bos=True)[1].cpu()
-        return out["input_features"], lab
+        return out["input_features"], lab_d.cpu()
 
     for _ in range(2):
         feats_h, lab_h = host_step()
