@@ -371,6 +371,9 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
     float* const sig = sigbuf + (it & 1) * kSigBuf;
 
     WFE_TRACE(0);
+    // the fix-ups decided during the previous tile were published by its S4.  They are read HERE, before S1: on a silent
+    // tile there is no S2, so warp 7 may reach its bookkeeping block (which rewrites s_fix) straight after S1
+    const FixEntry fx0 = s_fix[0], fx1 = s_fix[1];
     // ---- top: start the NEXT tile's loads, then make sure this tile's signal has landed ----
     uint32_t idB = 0;
     if (sched) idB = atomicAdd(p.tile_counter, 1u);  // id of tile it+2, first used in this tile's stage 2
@@ -395,11 +398,8 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
 
     // ---- clamp fix-ups decided during the previous tile (own tiles, L2-resident) ----
     if (!(WFE_EXP & 1)) {
-#pragma unroll
-      for (int f = 0; f < 2; ++f) {
-        const FixEntry fx = s_fix[f];
-        if (fx.tile >= 0) fix_tile(p.out, p.n_mel, p.n_frames, fx, warp, lane);
-      }
+      if (fx0.tile >= 0) fix_tile(p.out, p.n_mel, p.n_frames, fx0, warp, lane);
+      if (fx1.tile >= 0) fix_tile(p.out, p.n_mel, p.n_frames, fx1, warp, lane);
     }
 
     float tmax_y = -1.5f, tmin_y = 3.0e38f;
