@@ -78,7 +78,7 @@ struct wfe_handle {
   int mel_wrange[wfe::kMelWarps + 1] = {0};
   int ctas_per_sm[2] = {0, 0};   // resident CTAs of logmel_kernel<float>, <int16_t>
   float4* d_s1_consts = nullptr;       // [8][25]
-  int4* d_mel_tab = nullptr;             // [n_rows][2][2]
+  float4* d_mel_tab = nullptr;           // [n_rows][2 halves]
   wfe::MelGroup* d_mel_groups = nullptr; // [n_groups]
   std::mutex host_mu;
   bool ring_ready = false;
@@ -262,88 +262,92 @@ int wfe_create(const wfe_config* cfg, const float* mel_filters, wfe_handle** out
   h->sm_count = prop.multiProcessorCount;
 
   // ---- mel projection tables (banded filter bank).  Mels are taken two at a time (m, m+1: one per half-warp); pairs
-  // are sorted by non-zero count and cut into groups of four "slots" that run in lock step over a common number of
-  // table rows (zero-weight padding up to the group's longest filter), so each thread carries four independent
-  // accumulators.  A table row holds, per half and slot, (float offset of the bin's row in the power buffer, weight).
+  // are sorted by band length and cut into groups of four "slots" that run in lock step over a common number of table
+  // rows, so each thread carries four independent accumulators.  Every (slot, half) filter is treated as a contiguous
+  // band of `trips` power rows [lo, lo + trips) (weights taken straight from the dense filter matrix, so zeros inside or
+  // beyond the filter cost nothing extra); a table row holds, per half, the four weights of the slots.
   const int n_mel = cfg->n_mel;
-  struct Nz {
-    int k;
-    float w;
+  struct Band {
+    int lo, len;
   };
-  std::vector<std::vector<Nz>> nz(n_mel + 1);
-  for (int m = 0; m < n_mel; ++m)
+  std::vector<Band> band(n_mel + 1, Band{0, 0});
+  for (int m = 0; m < n_mel; ++m) {
+    int first = -1, last = -1;
     for (int k = 0; k < wfe::kBins; ++k) {
       const float w = mel_filters[(size_t)k * n_mel + m];
-      if (w != 0.0f) nz[m].push_back({k, w});
+      if (!(w >= 0.0f)) {  // the tile extrema are tracked on the bit patterns of the mel powers, which must be >= 0
+        delete h;
+        return fail(WFE_ERR_UNSUPPORTED, "mel_filters must be non-negative and finite");
+      }
+      if (w != 0.0f) {
+        if (first < 0) first = k;
+        last = k;
+      }
     }
+    if (first >= 0) band[m] = Band{first, last - first + 1};
+  }
   struct PairN {
     int m, n;
   };
   std::vector<PairN> prs;
-  for (int m = 0; m < n_mel; m += 2) {
-    const int n = (int)(nz[m].size() > nz[m + 1].size() ? nz[m].size() : nz[m + 1].size());
-    prs.push_back({m, n});
-  }
+  for (int m = 0; m < n_mel; m += 2) prs.push_back({m, std::max(band[m].len, band[m + 1].len)});
   std::sort(prs.begin(), prs.end(), [](const PairN& a, const PairN& b) { return a.n != b.n ? a.n > b.n : a.m < b.m; });
   struct GroupCost {
-    int first, cost;  // first pair (index into prs), issue-slot estimate
+    int first, trips, cost;  // first pair (index into prs), table rows, issue-slot estimate
   };
   std::vector<GroupCost> gpool;
-  for (size_t i = 0; i < prs.size(); i += 4) gpool.push_back({(int)i, 14 * (prs[i].n < 1 ? 1 : prs[i].n) + 50});
-  std::vector<std::vector<int>> per_warp(wfe::kMelWarps);
+  for (size_t i = 0; i < prs.size(); i += 4) {
+    const int trips = std::max(2, (prs[i].n + 1) & ~1);  // even: the loop takes two rows per step
+    gpool.push_back({(int)i, trips, 10 * trips + 60});
+  }
+  std::vector<std::vector<GroupCost>> per_warp(wfe::kMelWarps);
   int load[wfe::kMelWarps] = {0};
   for (const GroupCost& gc : gpool) {  // longest-processing-time first (gpool is already sorted by cost, descending)
     int w = 0;
     for (int i = 1; i < wfe::kMelWarps; ++i)
       if (load[i] < load[w]) w = i;
-    per_warp[w].push_back(gc.first);
+    per_warp[w].push_back(gc);
     load[w] += gc.cost;
   }
-  std::vector<int4> mtab;
+  std::vector<float4> mtab;
   std::vector<wfe::MelGroup> groups;
   for (int w = 0; w < wfe::kMelWarps; ++w) {
     h->mel_wrange[w] = (int)groups.size();
-    for (int first : per_warp[w]) {
+    for (const GroupCost& gc : per_warp[w]) {
       wfe::MelGroup g;
-      g.trips = prs[first].n < 1 ? 1 : prs[first].n;
+      memset(&g, 0, sizeof(g));
+      g.trips = gc.trips;
       g.tab_idx = (int32_t)mtab.size();
-      g.valid = 0;
-      g.pad_ = 0;
-      int mel_of[4];
+      int mel_of[4], lo_of[2][4];
       for (int sl = 0; sl < 4; ++sl) {
-        const bool real = first + sl < (int)prs.size();
-        mel_of[sl] = real ? prs[first + sl].m : -1;
+        const bool real = gc.first + sl < (int)prs.size();
+        mel_of[sl] = real ? prs[gc.first + sl].m : -1;
         g.out_off[sl] = real ? mel_of[sl] * h->n_frames : 0;
         if (real) g.valid |= 1 << (2 * sl);
         if (real && mel_of[sl] + 1 < n_mel) g.valid |= 1 << (2 * sl + 1);
+        for (int half = 0; half < 2; ++half) {
+          // the band window must stay inside the 201 power rows of THIS tile (rows beyond hold stale data)
+          const int lo = real ? band[mel_of[sl] + half].lo : 0;
+          lo_of[half][sl] = std::max(0, std::min(lo, wfe::kBins - gc.trips));
+          g.lo_off[half][sl] = lo_of[half][sl] * wfe::kPStride;
+        }
       }
-      for (int i = 0; i < g.trips; ++i)
-        for (int half = 0; half < 2; ++half)
-          for (int sp = 0; sp < 2; ++sp) {  // one int4 = slots 2sp, 2sp+1
-            int4 row;
-            int* r = &row.x;
-            for (int j = 0; j < 2; ++j) {
-              const int sl = 2 * sp + j;
-              int k = 0;
-              float wgt = 0.0f;
-              if (mel_of[sl] >= 0) {
-                const std::vector<Nz>& v = nz[mel_of[sl] + half];
-                if (i < (int)v.size()) {
-                  k = v[i].k;
-                  wgt = v[i].w;
-                }
-              }
-              r[2 * j] = k * wfe::kPStride;
-              memcpy(&r[2 * j + 1], &wgt, sizeof(float));
-            }
-            mtab.push_back(row);
+      for (int i = 0; i < gc.trips; ++i)
+        for (int half = 0; half < 2; ++half) {
+          float wgt[4];
+          for (int sl = 0; sl < 4; ++sl) {
+            const int m = mel_of[sl] >= 0 ? mel_of[sl] + half : -1;
+            const int k = lo_of[half][sl] + i;
+            wgt[sl] = (m >= 0 && m < n_mel && k < wfe::kBins) ? mel_filters[(size_t)k * n_mel + m] : 0.0f;
           }
+          mtab.push_back(make_float4(wgt[0], wgt[1], wgt[2], wgt[3]));
+        }
       groups.push_back(g);
     }
   }
   h->mel_wrange[wfe::kMelWarps] = (int)groups.size();
   h->n_groups = (int)groups.size();
-  h->n_rows = (int)(mtab.size() / 4);
+  h->n_rows = (int)(mtab.size() / 2);
   if (h->n_groups > wfe::kMaxMelGroups || h->n_rows > wfe::kMaxMelRows) {
     delete h;
     return fail(WFE_ERR_UNSUPPORTED, "mel filter bank has too many non-zeros (not banded)");
@@ -351,13 +355,13 @@ int wfe_create(const wfe_config* cfg, const float* mel_filters, wfe_handle** out
   std::vector<float> s1c(8 * wfe::kS1ConstVec * 4);
   wfe::fill_stage1_consts(s1c.data());
   if (cudaMalloc((void**)&h->d_s1_consts, s1c.size() * sizeof(float)) != cudaSuccess ||
-      cudaMalloc((void**)&h->d_mel_tab, mtab.size() * sizeof(int4)) != cudaSuccess ||
+      cudaMalloc((void**)&h->d_mel_tab, mtab.size() * sizeof(float4)) != cudaSuccess ||
       cudaMalloc((void**)&h->d_mel_groups, groups.size() * sizeof(wfe::MelGroup)) != cudaSuccess) {
     wfe_destroy(h);
     return fail(WFE_ERR_NOMEM, "cudaMalloc failed for constant tables");
   }
   cudaMemcpy(h->d_s1_consts, s1c.data(), s1c.size() * sizeof(float), cudaMemcpyHostToDevice);
-  cudaMemcpy(h->d_mel_tab, mtab.data(), mtab.size() * sizeof(int4), cudaMemcpyHostToDevice);
+  cudaMemcpy(h->d_mel_tab, mtab.data(), mtab.size() * sizeof(float4), cudaMemcpyHostToDevice);
   cudaMemcpy(h->d_mel_groups, groups.data(), groups.size() * sizeof(wfe::MelGroup), cudaMemcpyHostToDevice);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {

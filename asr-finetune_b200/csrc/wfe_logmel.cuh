@@ -91,15 +91,18 @@ template <>
 __device__ __forceinline__ float pcm_to_float<int16_t>(int16_t v, float scale) { return (float)v * scale; }
 
 // one mel-stage work item: FOUR mel pairs (slot s: mels m_s, m_s+1, one per half-warp) that run in lock step over `trips`
-// table rows, so every thread has four independent accumulator chains.  Pairs are grouped by similar non-zero counts
-// (zero-weight padding up to the group's longest filter: 220 rows for 211 real ones on the large-v3 bank).
+// table rows, so every thread has four independent accumulator chains.  Every (slot, half) filter is a contiguous BAND of
+// `trips` power rows starting at row lo (zero weights where the band is longer than the filter), so the power loads are
+// pointer + immediate and a table row is just the four weights of a half.  Pairs are grouped by similar band length.
 struct alignas(16) MelGroup {
-  int32_t trips;       // table rows
-  int32_t tab_idx;     // index (in int4 units) of the group's first row; a row is [half][slot 0..3] x (offset, weight)
+  int32_t trips;       // table rows (even)
+  int32_t tab_idx;     // float4 index of the group's first row in mel_tab; row i = [half 0: w of slots 0..3][half 1: ...]
   int32_t valid;       // bit 2*s + h: mel of slot s, half h exists
   int32_t pad_;
   int32_t out_off[4];  // m_s * n_frames: element offset of slot s's first mel row inside one clip's output
+  int32_t lo_off[2][4];  // [half][slot]: lo * kPStride, float offset of the band's first power row
 };
+constexpr int kMelUnroll = 16;  // table rows per unrolled pass of the mel loop (large-v3's longest band: 16)
 
 struct LogmelParams {
   const void* pcm;
@@ -112,7 +115,7 @@ struct LogmelParams {
                             //     published (zero-initialised; keys of finite floats are never 0)
   uint32_t* tile_counter;   // [1] dynamic tile scheduler (zero-initialised)
   const float4* s1_consts;  // [8][25] per-warp window/twiddle block
-  const int4* mel_tab;      // [n_rows][2 halves][2] : (power-row float offset, weight bits) x 4 slots per half
+  const float4* mel_tab;    // [n_rows][2 halves]: the weights of slots 0..3
   const MelGroup* mel_groups;  // [n_groups], grouped by warp
   int mel_wrange[kMelWarps + 1];  // warp w < kMelWarps owns groups [mel_wrange[w], mel_wrange[w+1])
   float pcm_scale;
@@ -122,7 +125,7 @@ struct LogmelParams {
 
 constexpr int kSigBuf = (kSigSm + 3) & ~3;  // 16-byte multiple
 __host__ __device__ inline size_t logmel_smem_bytes(int n_rows) {
-  return (size_t)(2 * kSigBuf + kZSm) * 4 + 8 * kS1ConstVec * 16 + (size_t)n_rows * 4 * 16;
+  return (size_t)(2 * kSigBuf + kZSm) * 4 + 8 * kS1ConstVec * 16 + (size_t)n_rows * 2 * 16;
 }
 
 // work item handed from the scheduler lane to the CTA through shared memory
@@ -135,6 +138,7 @@ struct alignas(16) TileDesc {
   int64_t pad_;
 };
 constexpr int kModeSilent = 0, kModeAsync = 1, kModeSync = 2;
+constexpr int kSilentBit = 0x40000000;  // in a pending-ring tile index: the tile lies in the zero padding
 
 __device__ __forceinline__ void cp_async8(float* smem_dst, const void* gsrc) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
@@ -154,6 +158,9 @@ __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
 __device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v) {
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void st_global_f2(float* p, float x, float y) {
+  asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(x), "f"(y) : "memory");
+}
 // named barrier over the first `nthreads` threads' warps (id 1..15; 0 is __syncthreads)
 __device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -169,33 +176,62 @@ __device__ __forceinline__ float logmel_feature(float v) {
   return fmaxf(fmaf(lg2_approx(v), 0.25f * kLog10_2, 1.0f), -1.5f);
 }
 
+// the same without the floor: v = 0 gives -inf, which the per-clip clamp fix-up raises to max(floor, -1.5) later
+__device__ __forceinline__ float logmel_feature_raw(float v) { return fmaf(lg2_approx(v), 0.25f * kLog10_2, 1.0f); }
+
 struct FixEntry {
   int b, tile;       // tile < 0: nothing to do
-  float floor_y;     // ((g - 8) + 4) / 4 = y_max - 2
+  float floor_y;     // max(y_max - 2, -1.5): ((g - 8) + 4) / 4 and the absolute floor (log10(1e-10) + 4) / 4
   int silent;        // tile lies in the zero padding: store the constant instead of clamping
 };
 
-// apply the per-clip clamp to one of this CTA's own tiles (values come back from L2)
-__device__ __forceinline__ void fix_tile(float* __restrict__ out, int n_mel, int n_frames, const FixEntry fx, int warp,
-                                         int lane) {
+// apply the per-clip clamp to one of this CTA's own tiles (values come back from L2).  Executed by ONE warp for the mel
+// rows 4*(wi + nw*j) + (lane >> 3): eight lanes cover the 128 bytes a tile occupies in a mel row with 128-bit accesses,
+// eight rows in flight per thread.  In the main loop warp 7 does this alone (wi = 0, nw = 1) behind stages 2-3 of the
+// other warps, so the clamp never sits on the CTA's critical path; the kernel tail splits the rows over all warps.
+__device__ __forceinline__ void fix_tile(float* __restrict__ out, int n_mel, int n_frames, const FixEntry fx, int wi,
+                                         int nw, int lane) {
   const int t0 = fx.tile * kTileF;
-  if (t0 + lane >= n_frames) return;
-  float* q = out + ((size_t)fx.b * n_mel) * n_frames + t0 + lane;
-  if (fx.silent) {
-    const float y = fmaxf(-1.5f, fx.floor_y);  // (max(-10, g-8) + 4) / 4
-    for (int m = warp; m < n_mel; m += kWarps) q[(size_t)m * n_frames] = y;
-  } else {
-    for (int m0 = warp; m0 < n_mel; m0 += 4 * kWarps) {
-      float v[4];
+  const int nvalid = min(kTileF, n_frames - t0);
+  const float fl = fx.floor_y;
+  if ((n_frames & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
+    const int q = lane & 7, r = lane >> 3;
+    if (4 * q >= nvalid) return;  // nvalid is a multiple of 4 here
+    const size_t stride = (size_t)(n_frames >> 2);  // float4 per mel row
+    float4* const base = reinterpret_cast<float4*>(out + (size_t)fx.b * n_mel * n_frames + t0) + q;
+    const float4 c = make_float4(fl, fl, fl, fl);
+    for (int m0 = 4 * wi + r; m0 < n_mel; m0 += 32 * nw) {
+      if (fx.silent) {  // (max(-10, g-8) + 4) / 4 everywhere
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int m = m0 + j * kWarps;
-        v[j] = m < n_mel ? __ldcg(q + (size_t)m * n_frames) : 3.0e38f;
+        for (int j = 0; j < 8; ++j) {
+          const int m = m0 + 4 * nw * j;
+          if (m < n_mel) base[(size_t)m * stride] = c;
+        }
+      } else {
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int m = m0 + 4 * nw * j;
+          v[j] = m < n_mel ? __ldcg(base + (size_t)m * stride) : make_float4(3.0e38f, 3.0e38f, 3.0e38f, 3.0e38f);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int m = m0 + 4 * nw * j;
+          // (-inf, the log of a zero mel power, is below every floor)
+          if (fminf(fminf(v[j].x, v[j].y), fminf(v[j].z, v[j].w)) < fl)
+            base[(size_t)m * stride] = make_float4(fmaxf(v[j].x, fl), fmaxf(v[j].y, fl), fmaxf(v[j].z, fl), fmaxf(v[j].w, fl));
+        }
       }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int m = m0 + j * kWarps;
-        if (v[j] < fx.floor_y) q[(size_t)m * n_frames] = fx.floor_y;
+    }
+  } else {  // generic geometry: scalar, lane = frame
+    if (lane >= nvalid) return;
+    float* q = out + (size_t)fx.b * n_mel * n_frames + t0 + lane;
+    for (int m = wi; m < n_mel; m += nw) {
+      float* e = q + (size_t)m * n_frames;
+      if (fx.silent) {
+        *e = fl;
+      } else if (__ldcg(e) < fl) {
+        *e = fl;
       }
     }
   }
@@ -298,7 +334,7 @@ __device__ __forceinline__ void prefetch_signal(float* __restrict__ sig, const f
   if (r0 == 0 && c < (kSigLen - kRows * kHop) / 2) cp_async8(d + kRows * kSigStride, g + kRows * kHop);
 }
 
-// block (whole warp) until every tile of clip `b` has published its maximum; returns the clamp floor max - 2
+// block (whole warp) until every tile of clip `b` has published its maximum; returns the clamp floor max(max - 2, -1.5)
 __device__ __forceinline__ float wait_clip_floor(const LogmelParams& p, int b, int lane) {
   const uint32_t* row = p.tile_key + (size_t)b * p.ntiles;
   for (;;) {
@@ -310,8 +346,22 @@ __device__ __forceinline__ float wait_clip_floor(const LogmelParams& p, int b, i
       m = max(m, k);
     }
     m = __reduce_max_sync(0xffffffffu, m);
-    if (!__any_sync(0xffffffffu, zero)) return key2f(m) - 2.0f;
+    if (!__any_sync(0xffffffffu, zero)) return fmaxf(key2f(m) - 2.0f, -1.5f);
     __nanosleep(200);
+  }
+}
+
+// max / min of y over a tile from the per-warp extrema of the raw mel powers (warp-wide; result uniform)
+__device__ __forceinline__ void tile_extrema(const uint32_t (&red)[2][kWarps], int lane, int silent, float& mx, float& mn) {
+  uint32_t hi = lane < kMelWarps ? red[0][lane] : 0u;
+  uint32_t lo = lane < kMelWarps ? red[1][lane] : 0x7f800000u;
+  hi = __reduce_max_sync(0xffffffffu, hi);
+  lo = __reduce_min_sync(0xffffffffu, lo);
+  mx = logmel_feature_raw(__uint_as_float(hi));
+  mn = logmel_feature_raw(__uint_as_float(lo));
+  if (silent) {  // a tile in the zero padding: max = (log10(1e-10) + 4) / 4; min = -inf so that it is always written
+    mx = -1.5f;
+    mn = -__int_as_float(0x7f800000);
   }
 }
 
@@ -321,16 +371,16 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
   float* const sigbuf = smem;               // two signal staging buffers (tile i -> buffer i & 1)
   float* const zbuf = smem + 2 * kSigBuf;   // stage 1 -> stage 2 exchange; the power buffer aliases it after stage 2
   float4* const s_cst = reinterpret_cast<float4*>(zbuf + kZSm);
-  int4* const s_mtab = reinterpret_cast<int4*>(s_cst + 8 * kS1ConstVec);
+  float4* const s_mtab = reinterpret_cast<float4*>(s_cst + 8 * kS1ConstVec);
   __shared__ MelGroup s_groups[kMaxMelGroups];
-  __shared__ float s_red[2][2][kWarps];  // [tile parity][max, min][warp]
+  __shared__ uint32_t s_red[2][2][kWarps];  // [tile parity][max, min][warp]: bit patterns of the largest / smallest mel
+                                            // power of the tile (mel powers are >= 0, so uint order == float order)
   __shared__ TileDesc s_desc[2];         // descriptor of tile k lives in slot k & 1
-  __shared__ FixEntry s_fix[2];
-  __shared__ int2 s_pend_bt[kRing];      // (clip, tile)
-  __shared__ float s_pend_min[kRing];    // tile minimum of y; -inf marks a silent (not yet written) tile
+  __shared__ FixEntry s_fix[1];          // kernel tail only: the entry all warps work on
+  __shared__ int2 s_pend_bt[kRing];      // (clip, tile | kSilentBit: tile lies in the zero padding, not yet written)
+  __shared__ float s_pend_min[kRing];    // tile minimum of y (-inf when a mel power is 0)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float kNegInf = -__int_as_float(0x7f800000);
   const bool sched = tid == 7 * 32;  // lane 0 of warp 7: tile scheduler; the whole of warp 7 keeps the clamp's books
 
   // warp-7 state (uniform across its lanes): ring of this CTA's pending tiles and the previous tile, whose maximum is
@@ -342,7 +392,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
   // ---- one-time CTA set-up ----
   for (int i = tid; i < 8 * kS1ConstVec; i += kThreads) s_cst[i] = p.s1_consts[i];
   for (int i = tid; i < p.n_groups; i += kThreads) s_groups[i] = p.mel_groups[i];
-  for (int i = tid; i < p.n_rows * 4; i += kThreads) s_mtab[i] = p.mel_tab[i];
+  for (int i = tid; i < p.n_rows * 2; i += kThreads) s_mtab[i] = p.mel_tab[i];
   if (sched) {
     const uint32_t id0 = atomicAdd(p.tile_counter, 1u);
     const uint32_t id1 = atomicAdd(p.tile_counter, 1u);
@@ -351,8 +401,6 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
     s_desc[0] = make_desc<T>(p, id0, o, a);
     request_clip(p, id1, o, a);
     s_desc[1] = make_desc<T>(p, id1, o, a);
-    s_fix[0].tile = -1;
-    s_fix[1].tile = -1;
   }
   __syncthreads();
 
@@ -371,9 +419,6 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
     float* const sig = sigbuf + (it & 1) * kSigBuf;
 
     WFE_TRACE(0);
-    // the fix-ups decided during the previous tile were published by its S4.  They are read HERE, before S1: on a silent
-    // tile there is no S2, so warp 7 may reach its bookkeeping block (which rewrites s_fix) straight after S1
-    const FixEntry fx0 = s_fix[0], fx1 = s_fix[1];
     // ---- top: start the NEXT tile's loads, then make sure this tile's signal has landed ----
     uint32_t idB = 0;
     if (sched) idB = atomicAdd(p.tile_counter, 1u);  // id of tile it+2, first used in this tile's stage 2
@@ -393,16 +438,10 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
     if (p.mask != nullptr && tid < nvalid) p.mask[(size_t)b * p.n_frames + t0 + tid] = ((t0 + tid) * kHop < len) ? 1 : 0;
     cp_async_wait<1>();  // everything but the group just committed (= this tile's signal) is complete
     WFE_TRACE(1);
-    __syncthreads();     // S1: signal visible to all warps; s_fix / s_desc from the previous stage 2 published
+    __syncthreads();     // S1: signal visible to all warps
     WFE_TRACE(2);
 
-    // ---- clamp fix-ups decided during the previous tile (own tiles, L2-resident) ----
-    if (!(WFE_EXP & 1)) {
-      if (fx0.tile >= 0) fix_tile(p.out, p.n_mel, p.n_frames, fx0, warp, lane);
-      if (fx1.tile >= 0) fix_tile(p.out, p.n_mel, p.n_frames, fx1, warp, lane);
-    }
-
-    float tmax_y = -1.5f, tmin_y = 3.0e38f;
+    uint32_t rmax = 0u, rmin = 0x7f800000u;  // bit patterns of the largest / smallest mel power (identity: 0, +inf)
     if (!silent) {
       // ---- stage 1: warp w owns n1 = 2w, 2w+1 ----
       WFE_TRACE(3);
@@ -438,20 +477,10 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
         k1[j] = (chk1 >= 0 && w < p.ntiles) ? ld_relaxed_u32(p.tile_key + (size_t)chk1 * p.ntiles + w) : 1u;
       }
       WFE_TRACE_S(1);
-      // (2) previous tile: max / min over the 7 mel warps (three shuffles), publish the max, remember the tile
+      // (2) previous tile: max / min over the 7 mel warps, publish the max, remember the tile
       if (prev_b >= 0) {
-        const int pp = (it + 1) & 1;
-        float mx = lane < kMelWarps ? s_red[pp][0][lane] : -3.0e38f;
-        float mn = lane < kMelWarps ? s_red[pp][1][lane] : 3.0e38f;
-#pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {
-          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-          mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        }
-        if (prev_silent) {  // max = (log10(1e-10)+4)/4, min marker = -inf
-          mx = -1.5f;
-          mn = kNegInf;
-        }
+        float mx, mn;
+        tile_extrema(s_red[(it + 1) & 1], lane, prev_silent, mx, mn);
         // ring full: cannot happen while ntiles <= kRing unless other CTAs lag a whole clip behind; the oldest entry's
         // clip then has every tile assigned to a RUNNING CTA (ids are handed out in order) whose warp 7 publishes
         // without ever waiting, so this wait terminates
@@ -462,14 +491,14 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
           --ring_count;
           const float fl = wait_clip_floor(p, bt.x, lane);
           if (pm < fl) {
-            const FixEntry fx{bt.x, bt.y, fl, pm == kNegInf};
-            for (int w = 0; w < kWarps; ++w) fix_tile(p.out, p.n_mel, p.n_frames, fx, w, lane);
+            const FixEntry fx{bt.x, bt.y & ~kSilentBit, fl, (bt.y & kSilentBit) != 0};
+            fix_tile(p.out, p.n_mel, p.n_frames, fx, 0, 1, lane);
           }
         }
         if (lane == 0) {
           st_relaxed_u32(p.tile_key + (size_t)prev_b * p.ntiles + prev_tile, f2key(mx));
           const int slot = (ring_head + ring_count) & (kRing - 1);
-          s_pend_bt[slot] = make_int2(prev_b, prev_tile);
+          s_pend_bt[slot] = make_int2(prev_b, prev_tile | (prev_silent ? kSilentBit : 0));
           s_pend_min[slot] = mn;
         }
         ++ring_count;
@@ -479,39 +508,36 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
       prev_silent = silent;
       WFE_TRACE_S(2);
       // (3) consume the words: a clip is complete when none of them is zero; its max is the max of the words
-      int nfix = 0;
+      FixEntry fxa{0, -1, 0.f, 0}, fxb{0, -1, 0.f, 0};
       if (!(WFE_EXP & 16)) {
         const uint32_t m0 = __reduce_max_sync(0xffffffffu, max(max(k0[0], k0[1]), max(k0[2], k0[3])));
         const bool z0 = __any_sync(0xffffffffu, (k0[0] == 0) | (k0[1] == 0) | (k0[2] == 0) | (k0[3] == 0));
         const uint32_t m1 = __reduce_max_sync(0xffffffffu, max(max(k1[0], k1[1]), max(k1[2], k1[3])));
         const bool z1 = __any_sync(0xffffffffu, (k1[0] == 0) | (k1[1] == 0) | (k1[2] == 0) | (k1[3] == 0));
         if (chk0 >= 0 && !z0) {
-          const float floor_y = key2f(m0) - 2.0f;
+          const float floor_y = fmaxf(key2f(m0) - 2.0f, -1.5f);
           const int2 bt = s_pend_bt[ring_head];
           const float pm = s_pend_min[ring_head];
           ring_head = (ring_head + 1) & (kRing - 1);
           --ring_count;
-          if (pm < floor_y) {
-            if (lane == 0) s_fix[nfix] = FixEntry{bt.x, bt.y, floor_y, pm == kNegInf};
-            ++nfix;
-          }
+          if (pm < floor_y) fxa = FixEntry{bt.x, bt.y & ~kSilentBit, floor_y, (bt.y & kSilentBit) != 0};
           if (chk1 >= 0 && !z1) {
-            const float floor1 = key2f(m1) - 2.0f;
+            const float floor1 = fmaxf(key2f(m1) - 2.0f, -1.5f);
             const int2 bt1 = s_pend_bt[ring_head];
             const float pm1 = s_pend_min[ring_head];
             ring_head = (ring_head + 1) & (kRing - 1);
             --ring_count;
-            if (pm1 < floor1) {
-              if (lane == 0) s_fix[nfix] = FixEntry{bt1.x, bt1.y, floor1, pm1 == kNegInf};
-              ++nfix;
-            }
+            if (pm1 < floor1) fxb = FixEntry{bt1.x, bt1.y & ~kSilentBit, floor1, (bt1.y & kSilentBit) != 0};
           }
         }
       }
-      if (lane == 0) {
-        for (int f = nfix; f < 2; ++f) s_fix[f].tile = -1;
-        // (4) hand tile it+2 to the CTA (slot of tile it, whose descriptor already sits in registers)
-        s_desc[it & 1] = make_desc<T>(p, idB, g_off, g_avail);
+      // (4) hand tile it+2 to the CTA (slot of tile it, whose descriptor already sits in registers)
+      if (lane == 0) s_desc[it & 1] = make_desc<T>(p, idB, g_off, g_avail);
+      // (5) the clamp fix-ups just decided (own tiles, written at least two tiles ago, L2-resident): warp 7 alone,
+      //     behind stages 2-3 of the other warps
+      if (!(WFE_EXP & 1)) {
+        if (fxa.tile >= 0) fix_tile(p.out, p.n_mel, p.n_frames, fxa, 0, 1, lane);
+        if (fxb.tile >= 0) fix_tile(p.out, p.n_mel, p.n_frames, fxb, 0, 1, lane);
       }
       WFE_TRACE_S(3);
       WFE_TRACE_S(4);
@@ -533,58 +559,83 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
                                           // scheduler block overlaps stages 2 and 3
       WFE_TRACE(8);
       // ---- stage 3: banded mel projection, exact fp32.  Half-warp h owns mel m_s + h of each of a group's four slots,
-      //      lane pr owns frames 2pr, 2pr+1.  Per table row: 2 LDS.128 (4 x (offset, weight)), 4 LDS.64 (power pairs of
-      //      the two frames), 4 FFMA2 with the weight broadcast: four independent chains per thread ----
+      //      lane pr owns frames 2pr, 2pr+1.  Per table row: 1 broadcast LDS.128 (the four weights of this half), 4 LDS.64
+      //      (power pairs, band pointer + immediate), 4 FFMA2 with the weight broadcast: four independent chains per
+      //      thread.  Epilogue: lg2, one FFMA, 64-bit full-line stores; the tile's extrema are tracked on the RAW mel
+      //      powers as integers (>= 0, so uint order == float order): ALU pipe, not FMA, and one REDUX per warp ----
       if (!(WFE_EXP & 2)) {
         const int h = lane >> 4, pr = lane & 15;
-        const bool vec_ok = nvalid == kTileF && (p.n_frames & 1) == 0;
-        const float* const pw = zbuf + 2 * pr;  // power pair (frames 2pr, 2pr+1) of bin row 0
-        float* const obase = p.out + ((size_t)b * p.n_mel + h) * p.n_frames + t0 + 2 * pr;
+        const bool full = nvalid == kTileF && (p.n_frames & 1) == 0;
+        const float* const pwl = zbuf + 2 * pr;  // power pair (frames 2pr, 2pr+1) of bin row 0
+        float* obase = p.out + ((size_t)b * p.n_mel + h) * p.n_frames + t0 + 2 * pr;
+        asm volatile("" : "+l"(obase));  // keep it one 64-bit base: each store address is then a single IMAD.WIDE
         const int g_end = p.mel_wrange[warp + 1];
         for (int gi = p.mel_wrange[warp]; gi < g_end; ++gi) {
-          const int4 gd = *reinterpret_cast<const int4*>(&s_groups[gi]);            // trips, tab_idx, valid
-          const int4 go = *(reinterpret_cast<const int4*>(&s_groups[gi]) + 1);      // out_off[0..3]
-          const int4* e = s_mtab + gd.y + 2 * h;
+          const int4* const gp = reinterpret_cast<const int4*>(&s_groups[gi]);
+          const int4 gd = gp[0];      // trips, tab_idx, valid
+          const int4 go = gp[1];      // out_off[0..3]
+          const int4 lo = gp[2 + h];  // lo_off[h][0..3]
+          const float *p0 = pwl + lo.x, *p1 = pwl + lo.y, *p2 = pwl + lo.z, *p3 = pwl + lo.w;
+          const float4* wr = s_mtab + gd.y + h;
           f2 a0 = mk2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
-#pragma unroll 2
-          for (int i = 0; i < gd.x; ++i, e += 4) {
-            const int4 r0 = e[0], r1 = e[1];  // slots 0,1 and 2,3: (power-row float offset, weight) x 2
-            a0 = vfma(f2{*reinterpret_cast<const float2*>(pw + r0.x)}, __int_as_float(r0.y), a0);
-            a1 = vfma(f2{*reinterpret_cast<const float2*>(pw + r0.z)}, __int_as_float(r0.w), a1);
-            a2 = vfma(f2{*reinterpret_cast<const float2*>(pw + r1.x)}, __int_as_float(r1.y), a2);
-            a3 = vfma(f2{*reinterpret_cast<const float2*>(pw + r1.z)}, __int_as_float(r1.w), a3);
+          for (int rem = gd.x;;) {
+#pragma unroll
+            for (int i = 0; i < kMelUnroll; i += 2) {
+              if (i >= rem) break;
+              const float4 w0 = wr[2 * i], w1 = wr[2 * i + 2];
+              a0 = vfma(f2{*reinterpret_cast<const float2*>(p0 + i * kPStride)}, w0.x, a0);
+              a1 = vfma(f2{*reinterpret_cast<const float2*>(p1 + i * kPStride)}, w0.y, a1);
+              a2 = vfma(f2{*reinterpret_cast<const float2*>(p2 + i * kPStride)}, w0.z, a2);
+              a3 = vfma(f2{*reinterpret_cast<const float2*>(p3 + i * kPStride)}, w0.w, a3);
+              a0 = vfma(f2{*reinterpret_cast<const float2*>(p0 + (i + 1) * kPStride)}, w1.x, a0);
+              a1 = vfma(f2{*reinterpret_cast<const float2*>(p1 + (i + 1) * kPStride)}, w1.y, a1);
+              a2 = vfma(f2{*reinterpret_cast<const float2*>(p2 + (i + 1) * kPStride)}, w1.z, a2);
+              a3 = vfma(f2{*reinterpret_cast<const float2*>(p3 + (i + 1) * kPStride)}, w1.w, a3);
+            }
+            rem -= kMelUnroll;
+            if (rem <= 0) break;
+            p0 += kMelUnroll * kPStride;
+            p1 += kMelUnroll * kPStride;
+            p2 += kMelUnroll * kPStride;
+            p3 += kMelUnroll * kPStride;
+            wr += 2 * kMelUnroll;
           }
           const f2 acc[4] = {a0, a1, a2, a3};
-          const int off[4] = {go.x, go.y, go.z, go.w};
+          const uint32_t off[4] = {(uint32_t)go.x, (uint32_t)go.y, (uint32_t)go.z, (uint32_t)go.w};
+          if (full && gd.z == 0xff) {
 #pragma unroll
-          for (int sl = 0; sl < 4; ++sl) {
-            const float y0 = logmel_feature(acc[sl].v.x), y1 = logmel_feature(acc[sl].v.y);
-            float* q0 = obase + off[sl];
-            if ((gd.z >> (2 * sl + h)) & 1) {
-              if (vec_ok) {
-                *reinterpret_cast<float2*>(q0) = make_float2(y0, y1);
-                tmax_y = fmaxf(tmax_y, fmaxf(y0, y1));
-                tmin_y = fminf(tmin_y, fminf(y0, y1));
-              } else {
-                if (2 * pr < nvalid) { q0[0] = y0; tmax_y = fmaxf(tmax_y, y0); tmin_y = fminf(tmin_y, y0); }
-                if (2 * pr + 1 < nvalid) { q0[1] = y1; tmax_y = fmaxf(tmax_y, y1); tmin_y = fminf(tmin_y, y1); }
-              }
+            for (int sl = 0; sl < 4; ++sl) {
+              const uint32_t u0 = __float_as_uint(acc[sl].v.x), u1 = __float_as_uint(acc[sl].v.y);
+              rmax = max(rmax, max(u0, u1));
+              rmin = min(rmin, min(u0, u1));
+              st_global_f2(obase + off[sl], logmel_feature_raw(acc[sl].v.x), logmel_feature_raw(acc[sl].v.y));
+            }
+          } else {
+#pragma unroll
+            for (int sl = 0; sl < 4; ++sl) {
+              if (!((gd.z >> (2 * sl + h)) & 1)) continue;
+              float* q0 = obase + off[sl];
+              const float v[2] = {acc[sl].v.x, acc[sl].v.y};
+#pragma unroll
+              for (int e = 0; e < 2; ++e)
+                if (2 * pr + e < nvalid) {
+                  q0[e] = logmel_feature_raw(v[e]);
+                  rmax = max(rmax, __float_as_uint(v[e]));
+                  rmin = min(rmin, __float_as_uint(v[e]));
+                }
             }
           }
         }
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        tmax_y = fmaxf(tmax_y, __shfl_xor_sync(0xffffffffu, tmax_y, o));
-        tmin_y = fminf(tmin_y, __shfl_xor_sync(0xffffffffu, tmin_y, o));
-      }
+      rmax = __reduce_max_sync(0xffffffffu, rmax);
+      rmin = __reduce_min_sync(0xffffffffu, rmin);
       if (lane == 0) {
-        s_red[it & 1][0][warp] = tmax_y;
-        s_red[it & 1][1][warp] = tmin_y;
+        s_red[it & 1][0][warp] = rmax;
+        s_red[it & 1][1][warp] = rmin;
       }
     }
     WFE_TRACE(9);
-    __syncthreads();  // S4: tile written (visible to this CTA); s_desc / s_fix / s_red published; smem free
+    __syncthreads();  // S4: tile written (visible to this CTA); s_desc / s_red published; smem free
     WFE_TRACE(10);
     cur = nxt;
     nxt = s_desc[it & 1];
@@ -595,39 +646,23 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
   // ---- epilogue: publish the last tile, then drain the tiles this CTA still has pending (every remaining tile of their
   //      clips is owned by a running CTA whose warp 7 publishes without ever waiting: the waits terminate) ----
   if (warp == 7 && prev_b >= 0) {
-    const int pp = (it + 1) & 1;
-    float mx = lane < kMelWarps ? s_red[pp][0][lane] : -3.0e38f;
-    float mn = lane < kMelWarps ? s_red[pp][1][lane] : 3.0e38f;
-#pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    }
-    if (prev_silent) {
-      mx = -1.5f;
-      mn = kNegInf;
-    }
+    float mx, mn;
+    tile_extrema(s_red[(it + 1) & 1], lane, prev_silent, mx, mn);
     if (lane == 0) st_relaxed_u32(p.tile_key + (size_t)prev_b * p.ntiles + prev_tile, f2key(mx));
     if (ring_count < kRing) {
       if (lane == 0) {
         const int slot = (ring_head + ring_count) & (kRing - 1);
-        s_pend_bt[slot] = make_int2(prev_b, prev_tile);
+        s_pend_bt[slot] = make_int2(prev_b, prev_tile | (prev_silent ? kSilentBit : 0));
         s_pend_min[slot] = mn;
       }
       ++ring_count;
     } else {  // ring full (see above): fix this one with warp 7 alone once its clip completes
       const float fl = wait_clip_floor(p, prev_b, lane);
       if (mn < fl) {
-        const FixEntry fx{prev_b, prev_tile, fl, mn == kNegInf};
-        for (int w = 0; w < kWarps; ++w) fix_tile(p.out, p.n_mel, p.n_frames, fx, w, lane);
+        const FixEntry fx{prev_b, prev_tile, fl, prev_silent};
+        fix_tile(p.out, p.n_mel, p.n_frames, fx, 0, 1, lane);
       }
     }
-  }
-  // the fix-ups decided during the last tile's stage 2 were published by its S4
-#pragma unroll
-  for (int f = 0; f < 2; ++f) {
-    const FixEntry fx = s_fix[f];
-    if (fx.tile >= 0) fix_tile(p.out, p.n_mel, p.n_frames, fx, warp, lane);
   }
   __syncthreads();
   for (;;) {
@@ -639,7 +674,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
         ring_head = (ring_head + 1) & (kRing - 1);
         --ring_count;
         const float fl = wait_clip_floor(p, bt.x, lane);
-        if (lane == 0) s_fix[0] = FixEntry{bt.x, pm < fl ? bt.y : -1, fl, pm == kNegInf};
+        if (lane == 0) s_fix[0] = FixEntry{bt.x, pm < fl ? (bt.y & ~kSilentBit) : -1, fl, (bt.y & kSilentBit) != 0};
       } else if (lane == 0) {
         s_fix[0].tile = -2;  // -2: ring empty
       }
@@ -647,7 +682,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
     __syncthreads();
     const FixEntry fx = s_fix[0];
     if (fx.tile == -2) break;
-    if (fx.tile >= 0) fix_tile(p.out, p.n_mel, p.n_frames, fx, warp, lane);
+    if (fx.tile >= 0) fix_tile(p.out, p.n_mel, p.n_frames, fx, warp, kWarps, lane);
     __syncthreads();
   }
 }
