@@ -218,12 +218,6 @@ int retire_slot(wfe_handle* h, HostSlot& s) {
 
 extern "C" {
 
-#if WFE_EXP & 256
-// timing-trace build only: copy the device trace buffer out (not part of the shipped ABI)
-int wfe_debug_read_trace(unsigned long long* dst, int n) {
-  return (int)cudaMemcpyFromSymbol(dst, wfe::g_trace, sizeof(unsigned long long) * n);
-}
-#endif
 
 const char* wfe_last_error(void) { return g_err.c_str(); }
 int wfe_abi_version(void) { return WFE_ABI_VERSION; }
@@ -255,9 +249,9 @@ int wfe_create(const wfe_config* cfg, const float* mel_filters, wfe_handle** out
   h->n_frames = cfg->n_samples / wfe::kHop;
   h->ntiles = (h->n_frames + wfe::kTileF - 1) / wfe::kTileF;
 
-  if (h->ntiles > wfe::kRing) {
+  if (h->ntiles + 3 > wfe::kRing) {  // a CTA's pending ring must be able to hold more than one clip's tiles
     delete h;
-    return fail(WFE_ERR_UNSUPPORTED, "n_samples too long: at most 128 tiles of 32 frames (40.96 s) per clip");
+    return fail(WFE_ERR_UNSUPPORTED, "n_samples too long: at most 125 tiles of 32 frames (40 s) per clip");
   }
   h->sm_count = prop.multiProcessorCount;
 
