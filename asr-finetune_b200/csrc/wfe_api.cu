@@ -131,6 +131,13 @@ int launch_logmel(wfe_handle* h, const void* pcm, float scale, const int64_t* of
                                   (int)wfe::logmel_smem_bytes(wfe::kMaxMelRows)));
     WFE_CUDA(cudaFuncSetAttribute(wfe::logmel_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                   cudaSharedmemCarveoutMaxShared));
+    // the kernel's warps re-partition the CTA's register pool (setmaxnreg): the pool is threads x the COMPILED register
+    // count, which must cover the budget or the growing warps would wait forever
+    cudaFuncAttributes fa;
+    WFE_CUDA(cudaFuncGetAttributes(&fa, wfe::logmel_kernel<T>));
+    if (fa.numRegs * wfe::kThreads < wfe::kRegsBudget)
+      return fail(WFE_ERR_UNSUPPORTED, "logmel kernel was compiled with " + std::to_string(fa.numRegs) +
+                                           " registers per thread: too few for its register budget");
     int n = 0;
     WFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, wfe::logmel_kernel<T>, wfe::kThreads, smem));
     if (n < 1) return fail(WFE_ERR_CUDA, "logmel kernel does not fit on an SM");

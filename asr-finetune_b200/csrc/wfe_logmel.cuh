@@ -42,13 +42,25 @@
 
 namespace wfe {
 
-constexpr int kFftWarps = 8;
+constexpr int kFftTeams = 2;                   // team t takes the pipeline tiles n = t (mod 2)
+constexpr int kTeamWarps = 8;
+constexpr int kFftWarps = kFftTeams * kTeamWarps;
 constexpr int kMelWarps = 4;
 constexpr int kLWarp = kFftWarps + kMelWarps;  // loader warp
 constexpr int kKWarp = kLWarp + 1;             // bookkeeper warp
-constexpr int kWarps = kKWarp + 1;
-constexpr int kThreads = kWarps * 32;          // 448
-constexpr int kFftThreads = kFftWarps * 32;
+constexpr int kIdleWarps = 2;                  // only there to bring their registers into the CTA's pool (see below)
+constexpr int kWarps = kKWarp + 1 + kIdleWarps;
+constexpr int kThreads = kWarps * 32;          // 768 (24 warps: registers are allocated four warps at a time)
+constexpr int kFftThreads = kTeamWarps * 32;   // threads of one FFT team
+// register budget (setmaxnreg): 768 threads launch with 80 registers each (the host checks the compiled count).  The
+// pool a warp can grow from is its OWN SM sub-partition's (warp index mod 4): six warps x 32 x 80 = 15360 registers,
+// shared by four FFT warps (88 each) and two others -- one mel warp (64) plus the loader (40), the bookkeeper (64) or an
+// idle warp (24) that is only there to bring its registers in: 32 * (4*88 + 64 + 64) = 15360.
+constexpr int kRegsLaunch = 80, kRegsFft = 88, kRegsMel = 64, kRegsL = 40, kRegsK = 64, kRegsIdle = 24;
+static_assert(kFftWarps == 16 && kMelWarps == 4, "the per-sub-partition register budget assumes 4 FFT + 1 mel warp each");
+static_assert(4 * kRegsFft + kRegsMel + kRegsK <= 6 * kRegsLaunch && kRegsL <= kRegsK && kRegsIdle <= kRegsK,
+              "register budget of an SM sub-partition");
+constexpr int kRegsBudget = 32 * (kFftWarps * kRegsFft + kMelWarps * kRegsMel + kRegsL + kRegsK + kIdleWarps * kRegsIdle);
 constexpr int kSigLen = (kTileF - 1) * kHop + kNFft;  // 5360 padded-signal samples per tile
 constexpr int kSigBlocks = (kSigLen + kSigBlock - 1) / kSigBlock;  // 5 bulk copies per tile (4 x 5120 B + 960 B)
 constexpr int kSigBuf = kSigLen + kSigSkew * (kSigBlocks - 1);    // 5424 floats per signal buffer (16-byte multiple)
@@ -113,7 +125,7 @@ struct LogmelParams {
 };
 
 __host__ __device__ inline size_t logmel_smem_bytes(int n_rows) {
-  return (size_t)(kSigStages * kSigBuf + 2 * kZSm + 2 * kPSm) * 4 + 8 * kS1ConstVec * 16 + (size_t)n_rows * 2 * 16;
+  return (size_t)(kSigStages * kSigBuf + kFftTeams * kZSm + 2 * kPSm) * 4 + 8 * kS1ConstVec * 16 + (size_t)n_rows * 2 * 16;
 }
 
 // work item handed from the S warp to the teams through shared memory
@@ -131,6 +143,14 @@ constexpr int kSilentBit = 0x40000000;  // in a pending-ring tile index: the til
 
 // ---- mbarrier / bulk-copy primitives (PTX; CTA-local shared addresses) ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <int N>
+__device__ __forceinline__ void reg_grow() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void reg_shrink() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -213,7 +233,7 @@ struct FixEntry {
 
 // apply the per-clip clamp to one of this CTA's own tiles (values come back from L2).  Executed by ONE warp for the mel
 // rows 4*(wi + nw*j) + (lane >> 3): eight lanes cover the 128 bytes a tile occupies in a mel row with 128-bit accesses,
-// sixteen rows in flight per thread.  In the main loop the S warp does this alone (wi = 0, nw = 1) beside the teams, so
+// eight rows in flight per thread.  In the main loop the S warp does this alone (wi = 0, nw = 1) beside the teams, so
 // the clamp never sits on the pipeline's critical path; the kernel tail splits the rows over all warps.
 __device__ __forceinline__ void fix_tile(float* __restrict__ out, int n_mel, int n_frames, const FixEntry fx, int wi,
                                          int nw, int lane) {
@@ -226,7 +246,7 @@ __device__ __forceinline__ void fix_tile(float* __restrict__ out, int n_mel, int
     const size_t stride = (size_t)(n_frames >> 2);  // float4 per mel row
     float4* const base = reinterpret_cast<float4*>(out + (size_t)fx.b * n_mel * n_frames + t0) + q;
     const float4 c = make_float4(fl, fl, fl, fl);
-    constexpr int kDeep = 16;
+    constexpr int kDeep = 8;
     for (int m0 = 4 * wi + r; m0 < n_mel; m0 += 4 * kDeep * nw) {
       if (fx.silent) {  // (max(-10, g-8) + 4) / 4 everywhere
 #pragma unroll
@@ -363,15 +383,16 @@ __device__ __forceinline__ bool clip_floor_ready(const LogmelParams& p, int b, i
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelParams p) {
+  static_assert(kThreads * kRegsLaunch >= kRegsBudget, "register budget");
   extern __shared__ __align__(16) float smem[];
   float* const sigbuf = smem;                         // signal ring: tile n -> buffer n % kSigStages (bulk copies)
-  float* const zbuf = sigbuf + kSigStages * kSigBuf;  // stage 1 -> stage 2 exchange ring
-  float* const pbuf = zbuf + 2 * kZSm;                // power ring: stage 2 -> mel team
+  float* const zbuf = sigbuf + kSigStages * kSigBuf;  // stage 1 -> stage 2 exchange, one buffer per FFT team
+  float* const pbuf = zbuf + kFftTeams * kZSm;        // power ring: stage 2 -> mel team (tile n -> buffer n & 1)
   float4* const s_cst = reinterpret_cast<float4*>(pbuf + 2 * kPSm);
   float4* const s_mtab = s_cst + 8 * kS1ConstVec;
   __shared__ MelGroup s_groups[kMaxMelGroups];
   __shared__ TileDesc s_desc[kDescRing];               // descriptor of pipeline tile n lives in slot n & 7
-  __shared__ uint32_t s_ext[kDescRing][2][kMelWarps];  // [tile slot][max, min][mel warp]: bit patterns of the largest /
+  __shared__ uint32_t s_ext[kDescRing][2][8];  // [tile slot][max, min][mel warp]: bit patterns of the largest /
                                                        // smallest mel power of the tile (>= 0: uint order == float order)
   __shared__ float s_min8[kDescRing];    // K warp: minimum of y of a published, not yet booked tile
   __shared__ FixEntry s_fix[1];          // kernel tail only: the entry all warps work on
@@ -390,11 +411,11 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelParams 
 #pragma unroll
     for (int i = 0; i < kSigStages; ++i) {
       mbar_init(&s_sig_full[i], 1);            // L warp's arrive (+ the bulk copies' bytes)
-      mbar_init(&s_sig_empty[i], kFftWarps);   // every FFT warp has its samples in registers
+      mbar_init(&s_sig_empty[i], kTeamWarps);  // every warp of the tile's FFT team has its samples in registers
     }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_p_full[i], kFftWarps);      // every FFT warp has stored its power rows
+      mbar_init(&s_p_full[i], kTeamWarps);     // every warp of FFT team i has stored its power rows
       mbar_init(&s_p_empty[i], kMelWarps);     // every mel warp is done reading
     }
 #pragma unroll
@@ -406,21 +427,30 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelParams 
   }
   __syncthreads();
 
+  if (warp > kKWarp) {  // idle warps: hand their registers to the pool and wait for the end (no warp exits early)
+    reg_shrink<kRegsIdle>();
+    __syncthreads();
+    return;
+  }
   int ring_head = 0, ring_count = 0;  // K warp: ring of this CTA's pending tiles
 
   if (warp < kFftWarps) {
-    // =============================== FFT team ===============================
-    // lane l of warp w takes n1 pair (l & 7) ^ w: every warp covers all eight pairs, lanes l, l+8, l+16, l+24 share
+    // =============================== FFT teams ===============================
+    reg_grow<kRegsFft>();
+    const int team = warp / kTeamWarps, tw = warp % kTeamWarps, ttid = tid % kFftThreads;
+    const int bar0 = 1 + 3 * team;  // the team's named barriers: bar0 (staging), bar0 + 1 (z full), bar0 + 2 (z free)
+    // lane l of team warp w takes n1 pair (l & 7) ^ w: every warp covers all eight pairs, lanes l, l+8, l+16, l+24 share
     // one -- that keeps the 64-bit signal loads conflict-free on the block-padded layout (see wfe_codelets.cuh)
-    const int pj = (lane & 7) ^ warp;
+    const int pj = (lane & 7) ^ tw;
     const float4* const cst = s_cst + pj * kS1ConstVec;
     const int n1 = 2 * pj;
-    // stage-2 task: warp 0 -> k2 = 0 (real input, light), warp 4 -> none, the other six -> k2 pairs (a, a+1)
-    const int s2a = (warp & 3) == 0 ? 0 : 2 * (warp < 4 ? warp - 1 : warp - 2) + 1;
+    // stage-2 task: team warp 0 -> k2 = 0 (real input, light), 4 -> none, the other six -> k2 pairs (a, a+1)
+    const int s2a = (tw & 3) == 0 ? 0 : 2 * (tw < 4 ? tw - 1 : tw - 2) + 1;
     const int roff0 = kHop * lane + kSigSkew * (lane / 8), roff1 = kHop * lane + kSigSkew * ((lane + 1) / 8),
               roff2 = kHop * lane + kSigSkew * ((lane + 2) / 8);
-    for (uint32_t n = 0;; ++n) {
-      const int sb = n & 1;
+    float* const z = zbuf + team * kZSm + lane;
+    for (uint32_t n = team;; n += kFftTeams) {
+      const int sb = n & 1;  // == team
       const uint32_t par = (n >> 1) & 1;
       const int ss = n % kSigStages;
       mbar_wait(&s_sig_full[ss], (n / kSigStages) & 1);
@@ -437,14 +467,13 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelParams 
         const int s_begin = d.tile * kTileF * kHop - kNFft / 2;
         if (p.norm != nullptr) {
           const float2 st = __ldg(p.norm + d.b);
-          stage_signal<T, true>(sig, pcm, s_begin, d.len, p.n_samples, p.pcm_scale, st.x, st.y, tid);
+          stage_signal<T, true>(sig, pcm, s_begin, d.len, p.n_samples, p.pcm_scale, st.x, st.y, ttid);
         } else {
-          stage_signal<T, false>(sig, pcm, s_begin, d.len, p.n_samples, p.pcm_scale, 0.f, 1.f, tid);
+          stage_signal<T, false>(sig, pcm, s_begin, d.len, p.n_samples, p.pcm_scale, 0.f, 1.f, ttid);
         }
-        bar_sync_named(1, kFftThreads);
+        bar_sync_named(bar0, kFftThreads);
       }
       // ---- stage 1 ----
-      float* const z = zbuf + sb * kZSm + lane;
       if (!silent) {
         f2 x[25];
         const float* const rowp[3] = {sig + roff0, sig + roff1, sig + roff2};
@@ -455,29 +484,32 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelParams 
       } else if (lane == 0) {
         mbar_arrive(&s_sig_empty[ss]);
       }
-      bar_sync_named(2, kFftThreads);  // z[sb] complete.  It is rewritten by stage 1 of tile n + 2, which every warp
-                                       // reaches only through this barrier of tile n + 1, i.e. after its stage 2 of n
+      bar_sync_named(bar0 + 1, kFftThreads);  // the team's z buffer is complete
       // ---- stage 2 ----
       float* const P = pbuf + sb * kPSm + lane;
       f2 pw[16];
       if (!silent && !(WFE_EXP & 4)) {
         if (s2a > 0)
           stage2_pair_compute(z, s2a, pw);
-        else if (warp == 0)
+        else if (tw == 0)
           stage2_k0_compute(z, pw);
       }
-      mbar_wait(&s_p_empty[sb], par ^ 1);  // the mel team is done with tile n - 2
+      bar_sync_named(bar0 + 2, kFftThreads);  // every warp has read z: the next tile's stage 1 may overwrite it
+      mbar_wait(&s_p_empty[sb], par ^ 1);     // the mel team is done with tile n - 2
       if (!silent && !(WFE_EXP & 4)) {
         if (s2a > 0)
           stage2_pair_store(pw, s2a, P);
-        else if (warp == 0)
+        else if (tw == 0)
           stage2_k0_store(pw, P);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_p_full[sb]);
     }
+    __syncthreads();  // (end of kernel: no warp exits early)
+    return;  // the tail belongs to the K and mel warps
   } else if (warp < kLWarp) {
     // =============================== mel team ===============================
+    reg_shrink<kRegsMel>();
     const int mw = warp - kFftWarps;
     const int h = lane >> 4, pr = lane & 15;
     const int g_begin = p.mel_wrange[mw], g_end = p.mel_wrange[mw + 1];
@@ -573,6 +605,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelParams 
     }
   } else if (warp == kLWarp) {
     // =============================== L warp: tile ids, descriptors, signal loads ===============================
+    reg_shrink<kRegsL>();
     auto draw = [&]() -> uint32_t {  // kDrawBatch consecutive tile ids; lane 0 holds the first, the others a dummy
       return lane == 0 ? atomicAdd(p.tile_counter, (uint32_t)kDrawBatch) : 0u;
     };
@@ -636,9 +669,12 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelParams 
       availA = availB;
       bidB_raw = bidC_raw;
     }
-    issue(make_desc<T>(p, p.total_tiles, 0, 0));  // stop
+    for (int t = 0; t < kFftTeams; ++t) issue(make_desc<T>(p, p.total_tiles, 0, 0));  // one stop per FFT team
+    __syncthreads();  // (end of kernel)
+    return;
   } else {
     // =============================== K warp: the books of the per-clip clamp ===============================
+    reg_shrink<kRegsK>();
     uint32_t n = 0;      // next pipeline tile to take into the ring
     uint32_t n_pub = 0;  // next pipeline tile whose maximum is to be published (>= n)
     // publish the maxima of finished tiles, in order, possibly ahead of the ring (never blocks)
@@ -741,9 +777,12 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelParams 
     }
   }
 
-  // ---- tail: drain the tiles this CTA still has pending, all warps on each.  Every tile of this CTA is published by
-  //      now, and the other CTAs' K warps publish theirs without ever waiting on another CTA: the waits terminate ----
-  __syncthreads();
+  // ---- tail (K and mel warps): drain the tiles this CTA still has pending, five warps on each.  Every tile of this CTA
+  //      is published by now, and the other CTAs' K warps publish theirs without ever waiting on another CTA: the
+  //      waits terminate ----
+  constexpr int kTailThreads = (kMelWarps + 1) * 32;
+  const int tw = warp == kKWarp ? kMelWarps : warp - kFftWarps;
+  bar_sync_named(7, kTailThreads);
   for (;;) {
     if (warp == kKWarp) {
       if (ring_count > 0) {
@@ -759,12 +798,13 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelParams 
         s_fix[0].tile = -2;  // -2: ring empty
       }
     }
-    __syncthreads();
+    bar_sync_named(7, kTailThreads);
     const FixEntry fx = s_fix[0];
     if (fx.tile == -2) break;
-    if (fx.tile >= 0) fix_tile(p.out, p.n_mel, p.n_frames, fx, warp, kWarps, lane);
-    __syncthreads();
+    if (fx.tile >= 0) fix_tile(p.out, p.n_mel, p.n_frames, fx, tw, kMelWarps + 1, lane);
+    bar_sync_named(7, kTailThreads);
   }
+  __syncthreads();  // (end of kernel)
 }
 
 // ---- per-clip mean / rstd for do_normalize (HF:...feature_extraction_whisper.py:168-187) ------------
