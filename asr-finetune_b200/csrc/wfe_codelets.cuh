@@ -285,15 +285,15 @@ inline void fill_stage1_consts(float* out /* 8 * 25 * 4 */) {
 }
 
 // ---- stage 1 for one (frame, n1 pair): window, real DFT-25, W400 twiddle, scatter to the z planes ----
-// Signal tile layout in shared memory: the tile's 5360 samples in blocks of 8 hop rows (1280 samples, one bulk copy
-// each) with 16 floats of padding between blocks: sample n at n + 16 * (n / 1280).  Blocks stay 16-byte aligned, and a
-// warp's 64-bit loads are conflict-free when lane l works on n1 pair (l & 7) ^ warp: within a half-warp the eight pairs
-// spread the lanes over 16 banks and the block padding moves the other eight lanes to the other 16.
-constexpr int kSigBlock = 8 * kHop;
-constexpr int kSigSkew = 16;
+// Signal tile layout in shared memory: sample n of the tile at n + 2 * (n / 160), i.e. two floats of padding after every
+// hop row.  Frame f then starts at 162 * f, and a warp's 64-bit loads of the same sample of 32 consecutive frames are
+// conflict-free (162 = 2 mod 32: the sixteen lanes of a half-warp cover the 32 banks).  Rows are only 8-byte aligned, so
+// the tile is filled with 8-byte cp.async (LDGSTS) rather than bulk copies.
+constexpr int kSigBlock = kHop;
+constexpr int kSigSkew = 2;
 WFE_DEV int sig_pos(int n) { return n + kSigSkew * (n / kSigBlock); }
 // pointer q such that sample j of frame f sits at q[j] for every j in hop row r of the frame (j / 160 == r)
-WFE_DEV const float* sig_row_ptr(const float* sig, int f, int r) { return sig + kHop * f + kSigSkew * ((f + r) / 8); }
+WFE_DEV const float* sig_row_ptr(const float* sig, int f, int r) { return sig + kHop * f + kSigSkew * (f + r); }
 // rowp: sig_row_ptr of this frame for r = 0, 1, 2; cst: the constant block of n1 pair n1/2 (25 float4); x: the windowed
 // samples n1 + 16*n2 (.x) and n1 + 1 + 16*n2 (.y).
 WFE_DEV void stage1_load(const float* const (&rowp)[3], const float4* __restrict__ cst, int n1, f2 (&x)[25]) {

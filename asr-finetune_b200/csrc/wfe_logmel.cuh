@@ -45,25 +45,29 @@ namespace wfe {
 constexpr int kFftTeams = 2;                   // team t takes the pipeline tiles n = t (mod 2)
 constexpr int kTeamWarps = 8;
 constexpr int kFftWarps = kFftTeams * kTeamWarps;
-constexpr int kMelWarps = 4;
-constexpr int kLWarp = kFftWarps + kMelWarps;  // loader warp
+constexpr int kMelWarps = 6;                   // warps 16..19 and 22, 23 (one or two per SM sub-partition)
+constexpr int kLWarp = kFftWarps + 4;          // loader warp
 constexpr int kKWarp = kLWarp + 1;             // bookkeeper warp
-constexpr int kIdleWarps = 2;                  // only there to bring their registers into the CTA's pool (see below)
-constexpr int kWarps = kKWarp + 1 + kIdleWarps;
+constexpr int kIdleWarps = 0;                  // only there to bring their registers into the CTA's pool (see below)
+constexpr int kWarps = kKWarp + 3;
 constexpr int kThreads = kWarps * 32;          // 768 (24 warps: registers are allocated four warps at a time)
 constexpr int kFftThreads = kTeamWarps * 32;   // threads of one FFT team
 // register budget (setmaxnreg): 768 threads launch with 80 registers each (the host checks the compiled count).  The
 // pool a warp can grow from is its OWN SM sub-partition's (warp index mod 4): six warps x 32 x 80 = 15360 registers,
-// shared by four FFT warps (88 each) and two others -- one mel warp (64) plus the loader (40), the bookkeeper (64) or an
-// idle warp (24) that is only there to bring its registers in: 32 * (4*88 + 64 + 64) = 15360.
-constexpr int kRegsLaunch = 80, kRegsFft = 88, kRegsMel = 64, kRegsL = 40, kRegsK = 64, kRegsIdle = 24;
-static_assert(kFftWarps == 16 && kMelWarps == 4, "the per-sub-partition register budget assumes 4 FFT + 1 mel warp each");
-static_assert(4 * kRegsFft + kRegsMel + kRegsK <= 6 * kRegsLaunch && kRegsL <= kRegsK && kRegsIdle <= kRegsK,
+// shared by four FFT warps (88 each), one mel warp (64) and the loader (40), the bookkeeper (64) or a second mel warp:
+// 32 * (4*88 + 64 + 64) = 15360.
+constexpr int kRegsLaunch = 80, kRegsFft = 88, kRegsMel = 64, kRegsL = 40, kRegsK = 64;
+static_assert(kFftWarps == 16 && kWarps == 24, "the per-sub-partition register budget assumes 4 FFT + 2 other warps each");
+static_assert(4 * kRegsFft + kRegsMel + kRegsK <= 6 * kRegsLaunch && kRegsL <= kRegsK && kRegsMel <= kRegsK,
               "register budget of an SM sub-partition");
-constexpr int kRegsBudget = 32 * (kFftWarps * kRegsFft + kMelWarps * kRegsMel + kRegsL + kRegsK + kIdleWarps * kRegsIdle);
+// named barriers: 1..6 the FFT teams' own (3 each), 7 the tail, 8/9 "power buffer t full" (FFT team t arrives, the mel
+// team waits), 10/11 "power buffer t free" (the mel team arrives, FFT team t waits).  Hardware barriers park the waiting
+// warps; an mbarrier try_wait loop was measured to burn half of all issued instructions here.
+constexpr int kBarPFull = 8, kBarPFree = 10, kPBarThreads = (kTeamWarps + kMelWarps) * 32;
+constexpr int kRegsBudget = 32 * (kFftWarps * kRegsFft + kMelWarps * kRegsMel + kRegsL + kRegsK);
 constexpr int kSigLen = (kTileF - 1) * kHop + kNFft;  // 5360 padded-signal samples per tile
-constexpr int kSigBlocks = (kSigLen + kSigBlock - 1) / kSigBlock;  // 5 bulk copies per tile (4 x 5120 B + 960 B)
-constexpr int kSigBuf = kSigLen + kSigSkew * (kSigBlocks - 1);    // 5424 floats per signal buffer (16-byte multiple)
+constexpr int kSigRows = kSigLen / kHop;                               // 33 full hop rows (+ 80 samples)
+constexpr int kSigBuf = (kSigLen + kSigSkew * kSigRows + 3) & ~3;      // 5428 floats per signal buffer
 constexpr int kZSm = kZPlanes * 16 * kTileF;          // 12800 floats per z buffer
 constexpr int kPSm = kBins * kPStride;                // 6432 floats per power buffer
 constexpr int kRing = 128;                            // pending-tile ring
@@ -72,7 +76,6 @@ constexpr int kDrawBatch = 4;                         // consecutive tile ids pe
 constexpr int kDescRing = 8;                          // descriptors / extrema of the tiles in flight (<= 6, see S warp)
 constexpr int kMaxMelGroups = 32;                     // groups of 4 mel pairs (n_mel <= 256)
 constexpr int kMaxMelRows = 128;                      // table rows over all groups (56 for large-v3); bounded by smem
-constexpr int kMelUnroll = 16;  // table rows per unrolled pass of the mel loop (large-v3's longest band: 16)
 
 static_assert(kSigBuf % 4 == 0 && kZSm % 4 == 0 && kPSm % 4 == 0, "16-byte aligned buffers");
 
@@ -183,9 +186,26 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return done != 0;
 }
+// blocking wait: the suspend-time hint keeps the warp parked in hardware instead of spinning through the issue port
+// (a bare try_wait loop comes back every few hundred cycles: measured 130 loop trips per warp per tile)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
-  }
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "WFE_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+      "@P1 bra WFE_DONE;\n\t"
+      "bra WFE_WAIT;\n\t"
+      "WFE_DONE:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"(0x989680u)
+      : "memory");
+}
+// 8-byte asynchronous copy global -> shared (LDGSTS), no registers held
+__device__ __forceinline__ void cp_async8(float* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+// arrive on `bar` (without raising its pending count) once all of this thread's earlier cp.async have landed
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // 1-D bulk copy global -> shared (16-byte aligned both sides, size a multiple of 16), completion counted on `bar`
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -214,6 +234,11 @@ __device__ __forceinline__ void st_global_f2(float* p, float x, float y) {
 // named barrier over `nthreads` threads (id 1..15; 0 is __syncthreads)
 __device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// non-blocking arrival at a named barrier (the waiting side uses bar_sync_named with the same id and count)
+__device__ __forceinline__ void bar_arrive_named(int id, int nthreads) {
+  __threadfence_block();  // bar.arrive itself promises no memory ordering: make this thread's writes visible first
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ float lg2_approx(float x) {
   float r;
@@ -299,21 +324,17 @@ __device__ __forceinline__ void stage_signal(float* __restrict__ sig, const T* _
       const uint4 raw = __ldg(src4 + v);
       const T* e = reinterpret_cast<const T*>(&raw);
       const int i = v * kVec;
-      float* dst = sig + sig_pos(i);  // 1280 is a multiple of kVec: a vector never straddles a block
+      float* dst = sig + sig_pos(i);  // 160 is a multiple of kVec: a vector never straddles a hop row
 #pragma unroll
-      for (int j = 0; j < kVec; j += 4) {
-        float4 o;
+      for (int j = 0; j < kVec; j += 2) {
+        float2 o;
         o.x = pcm_to_float<T>(e[j], scale);
         o.y = pcm_to_float<T>(e[j + 1], scale);
-        o.z = pcm_to_float<T>(e[j + 2], scale);
-        o.w = pcm_to_float<T>(e[j + 3], scale);
         if (kNorm) {
           o.x = (o.x - mean) * rstd;
           o.y = (o.y - mean) * rstd;
-          o.z = (o.z - mean) * rstd;
-          o.w = (o.w - mean) * rstd;
         }
-        *reinterpret_cast<float4*>(dst + j) = o;
+        *reinterpret_cast<float2*>(dst + j) = o;
       }
     }
   } else {
@@ -358,7 +379,7 @@ __device__ __forceinline__ TileDesc make_desc(const LogmelParams& p, uint32_t id
   } else {
     const T* src = reinterpret_cast<const T*>(p.pcm) + d.off + s_begin;
     const bool async_ok = sizeof(T) == 4 && p.norm == nullptr && s_begin >= 0 && s_begin + kSigLen <= d.len &&
-                          (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
+                          (reinterpret_cast<uintptr_t>(src) & 7u) == 0;
     d.mode = async_ok ? kModeAsync : kModeSync;
   }
   return d;
@@ -381,6 +402,22 @@ __device__ __forceinline__ bool clip_floor_ready(const LogmelParams& p, int b, i
 }
 
 
+// TRIPS table rows of one mel group: per row one broadcast LDS.128 (the four weights of this half) and, per slot, one
+// LDS.64 (power pair of this lane's two frames, band pointer + immediate) and one FFMA2 with the weight broadcast
+template <int TRIPS>
+__device__ __forceinline__ void mel_rows(const float* __restrict__ p0, const float* __restrict__ p1,
+                                         const float* __restrict__ p2, const float* __restrict__ p3,
+                                         const float4* __restrict__ wr, f2& a0, f2& a1, f2& a2, f2& a3) {
+#pragma unroll
+  for (int i = 0; i < TRIPS; ++i) {
+    const float4 w = wr[2 * i];
+    a0 = vfma(f2{*reinterpret_cast<const float2*>(p0 + i * kPStride)}, w.x, a0);
+    a1 = vfma(f2{*reinterpret_cast<const float2*>(p1 + i * kPStride)}, w.y, a1);
+    a2 = vfma(f2{*reinterpret_cast<const float2*>(p2 + i * kPStride)}, w.z, a2);
+    a3 = vfma(f2{*reinterpret_cast<const float2*>(p3 + i * kPStride)}, w.w, a3);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelParams p) {
   static_assert(kThreads * kRegsLaunch >= kRegsBudget, "register budget");
@@ -398,8 +435,8 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelParams 
   __shared__ FixEntry s_fix[1];          // kernel tail only: the entry all warps work on
   __shared__ int2 s_pend_bt[kRing];      // (clip, tile | kSilentBit: tile lies in the zero padding, not yet written)
   __shared__ float s_pend_min[kRing];    // tile minimum of y (-inf when a mel power is 0)
-  __shared__ __align__(8) uint64_t s_sig_full[kSigStages], s_sig_empty[kSigStages], s_p_full[2], s_p_empty[2],
-      s_ext_full[kDescRing], s_booked[kDescRing];
+  __shared__ __align__(8) uint64_t s_sig_full[kSigStages], s_sig_empty[kSigStages], s_ext_full[kDescRing],
+      s_booked[kDescRing];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -410,13 +447,8 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelParams 
   if (tid == 0) {
 #pragma unroll
     for (int i = 0; i < kSigStages; ++i) {
-      mbar_init(&s_sig_full[i], 1);            // L warp's arrive (+ the bulk copies' bytes)
+      mbar_init(&s_sig_full[i], 32);           // every L-warp lane: its copies have landed (or there are none)
       mbar_init(&s_sig_empty[i], kTeamWarps);  // every warp of the tile's FFT team has its samples in registers
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_p_full[i], kTeamWarps);     // every warp of FFT team i has stored its power rows
-      mbar_init(&s_p_empty[i], kMelWarps);     // every mel warp is done reading
     }
 #pragma unroll
     for (int i = 0; i < kDescRing; ++i) {
@@ -427,11 +459,6 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelParams 
   }
   __syncthreads();
 
-  if (warp > kKWarp) {  // idle warps: hand their registers to the pool and wait for the end (no warp exits early)
-    reg_shrink<kRegsIdle>();
-    __syncthreads();
-    return;
-  }
   int ring_head = 0, ring_count = 0;  // K warp: ring of this CTA's pending tiles
 
   if (warp < kFftWarps) {
@@ -439,25 +466,21 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelParams 
     reg_grow<kRegsFft>();
     const int team = warp / kTeamWarps, tw = warp % kTeamWarps, ttid = tid % kFftThreads;
     const int bar0 = 1 + 3 * team;  // the team's named barriers: bar0 (staging), bar0 + 1 (z full), bar0 + 2 (z free)
-    // lane l of team warp w takes n1 pair (l & 7) ^ w: every warp covers all eight pairs, lanes l, l+8, l+16, l+24 share
-    // one -- that keeps the 64-bit signal loads conflict-free on the block-padded layout (see wfe_codelets.cuh)
-    const int pj = (lane & 7) ^ tw;
-    const float4* const cst = s_cst + pj * kS1ConstVec;
-    const int n1 = 2 * pj;
+    // team warp w takes the n1 pair (2w, 2w + 1) of every frame of the tile
+    const float4* const cst = s_cst + tw * kS1ConstVec;
+    const int n1 = 2 * tw;
     // stage-2 task: team warp 0 -> k2 = 0 (real input, light), 4 -> none, the other six -> k2 pairs (a, a+1)
     const int s2a = (tw & 3) == 0 ? 0 : 2 * (tw < 4 ? tw - 1 : tw - 2) + 1;
-    const int roff0 = kHop * lane + kSigSkew * (lane / 8), roff1 = kHop * lane + kSigSkew * ((lane + 1) / 8),
-              roff2 = kHop * lane + kSigSkew * ((lane + 2) / 8);
+    const int roff0 = (kHop + kSigSkew) * lane;  // frame `lane` starts here; + kSigSkew per hop row crossed
     float* const z = zbuf + team * kZSm + lane;
     for (uint32_t n = team;; n += kFftTeams) {
       const int sb = n & 1;  // == team
-      const uint32_t par = (n >> 1) & 1;
       const int ss = n % kSigStages;
       mbar_wait(&s_sig_full[ss], (n / kSigStages) & 1);
       const TileDesc d = s_desc[n & (kDescRing - 1)];
       if (d.b < 0) {  // no more work: pass the stop on to the mel team
-        mbar_wait(&s_p_empty[sb], par ^ 1);
-        if (lane == 0) mbar_arrive(&s_p_full[sb]);
+        if (n >= 2) bar_sync_named(kBarPFree + sb, kPBarThreads);
+        bar_arrive_named(kBarPFull + sb, kPBarThreads);
         break;
       }
       const bool silent = d.mode == kModeSilent;
@@ -476,7 +499,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelParams 
       // ---- stage 1 ----
       if (!silent) {
         f2 x[25];
-        const float* const rowp[3] = {sig + roff0, sig + roff1, sig + roff2};
+        const float* const rowp[3] = {sig + roff0, sig + roff0 + kSigSkew, sig + roff0 + 2 * kSigSkew};
         stage1_load(rowp, cst, n1, x);
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_sig_empty[ss]);  // the buffer may be refilled (tile n + kSigStages)
@@ -495,27 +518,26 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelParams 
           stage2_k0_compute(z, pw);
       }
       bar_sync_named(bar0 + 2, kFftThreads);  // every warp has read z: the next tile's stage 1 may overwrite it
-      mbar_wait(&s_p_empty[sb], par ^ 1);     // the mel team is done with tile n - 2
+      if (n >= 2) bar_sync_named(kBarPFree + sb, kPBarThreads);  // the mel team is done with tile n - 2
       if (!silent && !(WFE_EXP & 4)) {
         if (s2a > 0)
           stage2_pair_store(pw, s2a, P);
         else if (tw == 0)
           stage2_k0_store(pw, P);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_p_full[sb]);
+      bar_arrive_named(kBarPFull + sb, kPBarThreads);
     }
     __syncthreads();  // (end of kernel: no warp exits early)
     return;  // the tail belongs to the K and mel warps
-  } else if (warp < kLWarp) {
+  } else if (warp != kLWarp && warp != kKWarp) {
     // =============================== mel team ===============================
     reg_shrink<kRegsMel>();
-    const int mw = warp - kFftWarps;
+    const int mw = warp < kLWarp ? warp - kFftWarps : warp - kFftWarps - 2;
     const int h = lane >> 4, pr = lane & 15;
     const int g_begin = p.mel_wrange[mw], g_end = p.mel_wrange[mw + 1];
     for (uint32_t n = 0;; ++n) {
       const int sb = n & 1;
-      mbar_wait(&s_p_full[sb], (n >> 1) & 1);
+      bar_sync_named(kBarPFull + sb, kPBarThreads);
       const TileDesc d = s_desc[n & (kDescRing - 1)];
       if (d.b < 0) {  // pass the stop on to the K warp
         if (lane == 0) mbar_arrive(&s_ext_full[n & (kDescRing - 1)]);
@@ -542,27 +564,24 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelParams 
           const float *p0 = pwl + lo.x, *p1 = pwl + lo.y, *p2 = pwl + lo.z, *p3 = pwl + lo.w;
           const float4* wr = s_mtab + gd.y + h;
           f2 a0 = mk2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
-          for (int rem = gd.x;;) {
-#pragma unroll
-            for (int i = 0; i < kMelUnroll; i += 2) {
-              if (i >= rem) break;
-              const float4 w0 = wr[2 * i], w1 = wr[2 * i + 2];
-              a0 = vfma(f2{*reinterpret_cast<const float2*>(p0 + i * kPStride)}, w0.x, a0);
-              a1 = vfma(f2{*reinterpret_cast<const float2*>(p1 + i * kPStride)}, w0.y, a1);
-              a2 = vfma(f2{*reinterpret_cast<const float2*>(p2 + i * kPStride)}, w0.z, a2);
-              a3 = vfma(f2{*reinterpret_cast<const float2*>(p3 + i * kPStride)}, w0.w, a3);
-              a0 = vfma(f2{*reinterpret_cast<const float2*>(p0 + (i + 1) * kPStride)}, w1.x, a0);
-              a1 = vfma(f2{*reinterpret_cast<const float2*>(p1 + (i + 1) * kPStride)}, w1.y, a1);
-              a2 = vfma(f2{*reinterpret_cast<const float2*>(p2 + (i + 1) * kPStride)}, w1.z, a2);
-              a3 = vfma(f2{*reinterpret_cast<const float2*>(p3 + (i + 1) * kPStride)}, w1.w, a3);
-            }
-            rem -= kMelUnroll;
-            if (rem <= 0) break;
-            p0 += kMelUnroll * kPStride;
-            p1 += kMelUnroll * kPStride;
-            p2 += kMelUnroll * kPStride;
-            p3 += kMelUnroll * kPStride;
-            wr += 2 * kMelUnroll;
+          switch (gd.x) {  // straight-line code per band length: all of a group's loads can be in flight at once
+            case 2: mel_rows<2>(p0, p1, p2, p3, wr, a0, a1, a2, a3); break;
+            case 4: mel_rows<4>(p0, p1, p2, p3, wr, a0, a1, a2, a3); break;
+            case 6: mel_rows<6>(p0, p1, p2, p3, wr, a0, a1, a2, a3); break;
+            case 8: mel_rows<8>(p0, p1, p2, p3, wr, a0, a1, a2, a3); break;
+            case 10: mel_rows<10>(p0, p1, p2, p3, wr, a0, a1, a2, a3); break;
+            case 12: mel_rows<12>(p0, p1, p2, p3, wr, a0, a1, a2, a3); break;
+            case 14: mel_rows<14>(p0, p1, p2, p3, wr, a0, a1, a2, a3); break;
+            case 16: mel_rows<16>(p0, p1, p2, p3, wr, a0, a1, a2, a3); break;
+            default:
+              for (int rem = gd.x; rem > 0; rem -= 2) {
+                mel_rows<2>(p0, p1, p2, p3, wr, a0, a1, a2, a3);
+                p0 += 2 * kPStride;
+                p1 += 2 * kPStride;
+                p2 += 2 * kPStride;
+                p3 += 2 * kPStride;
+                wr += 4;
+              }
           }
           const f2 acc[4] = {a0, a1, a2, a3};
           const uint32_t off[4] = {(uint32_t)go.x, (uint32_t)go.y, (uint32_t)go.z, (uint32_t)go.w};
@@ -598,10 +617,8 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelParams 
         s_ext[n & (kDescRing - 1)][1][mw] = rmin;
       }
       __syncwarp();  // the lanes' stores of the tile are ordered before lane 0's arrives
-      if (lane == 0) {
-        mbar_arrive(&s_ext_full[n & (kDescRing - 1)]);
-        mbar_arrive(&s_p_empty[sb]);
-      }
+      if (lane == 0) mbar_arrive(&s_ext_full[n & (kDescRing - 1)]);
+      bar_arrive_named(kBarPFree + sb, kPBarThreads);
     }
   } else if (warp == kLWarp) {
     // =============================== L warp: tile ids, descriptors, signal loads ===============================
@@ -624,21 +641,28 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelParams 
       const int ds = n & (kDescRing - 1), ss = n % kSigStages;
       mbar_wait(&s_booked[ds], ((n >> 3) & 1) ^ 1);                 // K warp is done with tile n - 8
       mbar_wait(&s_sig_empty[ss], ((n / kSigStages) & 1) ^ 1);      // FFT team has tile n - kSigStages in registers
-      if (lane == 0) {
-        s_desc[ds] = d;
-        if (d.b >= 0 && d.mode == kModeAsync && !(WFE_EXP & 32)) {
-          // one lane issues the tile's five block copies back to back (UBLKCP is a uniform-datapath instruction)
-          mbar_arrive_expect_tx(&s_sig_full[ss], kSigLen * 4);
-          const char* src = reinterpret_cast<const char*>(reinterpret_cast<const float*>(p.pcm) + d.off +
-                                                          d.tile * kTileF * kHop - kNFft / 2);
-          const uint32_t dst = smem_u32(sigbuf + ss * kSigBuf), bar = smem_u32(&s_sig_full[ss]);
+      if (lane == 0) s_desc[ds] = d;
+      __syncwarp();
+      if (d.b >= 0 && d.mode == kModeAsync && !(WFE_EXP & 32)) {
+        // 2680 8-byte cp.async per tile, 84 per lane.  Two hop rows (160 float2) take five warp-wide copies; only in the
+        // third one do the lanes split between the rows, so every address is (one of two per-lane bases) + immediate.
+        const float* src = reinterpret_cast<const float*>(p.pcm) + d.off + d.tile * kTileF * kHop - kNFft / 2 + 2 * lane;
+        float* dstA = sigbuf + ss * kSigBuf + 2 * lane;
+        float* dstB = dstA + (lane >= 16 ? kSigSkew : 0);
 #pragma unroll
-          for (int k = 0; k < kSigBlocks; ++k)
-            bulk_g2s_u32(dst + k * (kSigBlock + kSigSkew) * 4, src + k * kSigBlock * 4,
-                         (k + 1 < kSigBlocks ? kSigBlock : kSigLen - k * kSigBlock) * 4, bar);
-        } else {
-          mbar_arrive(&s_sig_full[ss]);  // silent, team-staged or stop: nothing to copy
+        for (int g = 0; g < (kSigRows + 2) / 2; ++g) {
+          constexpr int kPairDst = 2 * (kHop + kSigSkew), kPairSrc = 2 * kHop;
+          // float2 index within the row pair: lane + 32 m; row 1 starts at index 80 (dst + kSigSkew)
+          const int valid = g * kPairSrc < kSigLen ? (kSigLen - g * kPairSrc) / 2 : 0;  // float2 left from this pair on
+          if (0 < valid) cp_async8(dstA + g * kPairDst, src + g * kPairSrc);
+          if (32 < valid) cp_async8(dstA + g * kPairDst + 64, src + g * kPairSrc + 64);
+          if (64 < valid && 64 + lane < valid) cp_async8(dstB + g * kPairDst + 128, src + g * kPairSrc + 128);
+          if (96 < valid && 96 + lane < valid) cp_async8(dstA + g * kPairDst + 192 + kSigSkew, src + g * kPairSrc + 192);
+          if (128 < valid && 128 + lane < valid) cp_async8(dstA + g * kPairDst + 256 + kSigSkew, src + g * kPairSrc + 256);
         }
+        cp_async_arrive(&s_sig_full[ss]);
+      } else {
+        mbar_arrive(&s_sig_full[ss]);  // silent, team-staged or stop: nothing to copy
       }
       __syncwarp();
       ++n;
@@ -777,11 +801,11 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelParams 
     }
   }
 
-  // ---- tail (K and mel warps): drain the tiles this CTA still has pending, five warps on each.  Every tile of this CTA
+  // ---- tail (K and mel warps): drain the tiles this CTA still has pending, seven warps on each.  Every tile of this CTA
   //      is published by now, and the other CTAs' K warps publish theirs without ever waiting on another CTA: the
   //      waits terminate ----
   constexpr int kTailThreads = (kMelWarps + 1) * 32;
-  const int tw = warp == kKWarp ? kMelWarps : warp - kFftWarps;
+  const int tw = warp == kKWarp ? kMelWarps : (warp < kLWarp ? warp - kFftWarps : warp - kFftWarps - 2);
   bar_sync_named(7, kTailThreads);
   for (;;) {
     if (warp == kKWarp) {

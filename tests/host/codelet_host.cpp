@@ -17,7 +17,7 @@ void codelet_tile_power(const float* sig, float* power) {
     fill_stage1_consts(cst);
     init = true;
   }
-  alignas(16) static float skew[5360 + kSigSkew * (5360 / kSigBlock + 1)];
+  alignas(16) static float skew[5360 + kSigSkew * (5360 / kSigBlock + 1) + 8];
   static float zbuf[kZPlanes * 16 * kTileF];
   static float pbuf[kBins * kPStride];
   memset(pbuf, 0, sizeof(pbuf));
