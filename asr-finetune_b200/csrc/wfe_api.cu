@@ -131,13 +131,6 @@ int launch_logmel(wfe_handle* h, const void* pcm, float scale, const int64_t* of
                                   (int)wfe::logmel_smem_bytes(wfe::kMaxMelRows)));
     WFE_CUDA(cudaFuncSetAttribute(wfe::logmel_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                   cudaSharedmemCarveoutMaxShared));
-    // the kernel's warps re-partition the CTA's register pool (setmaxnreg): the pool is threads x the COMPILED register
-    // count, which must cover the budget or the growing warps would wait forever
-    cudaFuncAttributes fa;
-    WFE_CUDA(cudaFuncGetAttributes(&fa, wfe::logmel_kernel<T>));
-    if (fa.numRegs * wfe::kThreads < wfe::kRegsBudget)
-      return fail(WFE_ERR_UNSUPPORTED, "logmel kernel was compiled with " + std::to_string(fa.numRegs) +
-                                           " registers per thread: too few for its register budget");
     int n = 0;
     WFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, wfe::logmel_kernel<T>, wfe::kThreads, smem));
     if (n < 1) return fail(WFE_ERR_CUDA, "logmel kernel does not fit on an SM");
@@ -225,6 +218,12 @@ int retire_slot(wfe_handle* h, HostSlot& s) {
 
 extern "C" {
 
+#if WFE_EXP & 256
+// timing-trace build only: copy the device trace buffer out (not part of the shipped ABI)
+int wfe_debug_read_trace(unsigned long long* dst, int n) {
+  return (int)cudaMemcpyFromSymbol(dst, wfe::g_trace, sizeof(unsigned long long) * n);
+}
+#endif
 
 const char* wfe_last_error(void) { return g_err.c_str(); }
 int wfe_abi_version(void) { return WFE_ABI_VERSION; }
@@ -256,9 +255,9 @@ int wfe_create(const wfe_config* cfg, const float* mel_filters, wfe_handle** out
   h->n_frames = cfg->n_samples / wfe::kHop;
   h->ntiles = (h->n_frames + wfe::kTileF - 1) / wfe::kTileF;
 
-  if (h->ntiles + 3 > wfe::kRing) {  // a CTA's pending ring must be able to hold more than one clip's tiles
+  if (h->ntiles > wfe::kRing) {
     delete h;
-    return fail(WFE_ERR_UNSUPPORTED, "n_samples too long: at most 125 tiles of 32 frames (40 s) per clip");
+    return fail(WFE_ERR_UNSUPPORTED, "n_samples too long: at most 128 tiles of 32 frames (40.96 s) per clip");
   }
   h->sm_count = prop.multiProcessorCount;
 

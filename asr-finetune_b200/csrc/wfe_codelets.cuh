@@ -285,35 +285,25 @@ inline void fill_stage1_consts(float* out /* 8 * 25 * 4 */) {
 }
 
 // ---- stage 1 for one (frame, n1 pair): window, real DFT-25, W400 twiddle, scatter to the z planes ----
-// Signal tile layout in shared memory: sample n of the tile at n + 2 * (n / 160), i.e. two floats of padding after every
-// hop row.  Frame f then starts at 162 * f, and a warp's 64-bit loads of the same sample of 32 consecutive frames are
-// conflict-free (162 = 2 mod 32: the sixteen lanes of a half-warp cover the 32 banks).  Rows are only 8-byte aligned, so
-// the tile is filled with 8-byte cp.async (LDGSTS) rather than bulk copies.
-constexpr int kSigBlock = kHop;
-constexpr int kSigSkew = 2;
-WFE_DEV int sig_pos(int n) { return n + kSigSkew * (n / kSigBlock); }
-// pointer q such that sample j of frame f sits at q[j] for every j in hop row r of the frame (j / 160 == r)
-WFE_DEV const float* sig_row_ptr(const float* sig, int f, int r) { return sig + kHop * f + kSigSkew * (f + r); }
-// rowp: sig_row_ptr of this frame for r = 0, 1, 2; cst: the constant block of n1 pair n1/2 (25 float4); x: the windowed
-// samples n1 + 16*n2 (.x) and n1 + 1 + 16*n2 (.y).
-WFE_DEV void stage1_load(const float* const (&rowp)[3], const float4* __restrict__ cst, int n1, f2 (&x)[25]) {
+// sig_frame: this frame's 400 samples in the skewed tile layout (sample n at n + 2*(n/160)), 8-byte aligned;
+// cst: the warp's constant block (25 float4, read as broadcast 128-bit loads); zcol = z + frame.
+WFE_DEV void stage1_pair(const float* __restrict__ sig_frame, const float4* __restrict__ cst, int n1,
+                         float* __restrict__ zcol) {
+  f2 x[25];
 #pragma unroll
   for (int j = 0; j < 13; ++j) {
     const float4 c = cst[j];
     {
       const int n2 = 2 * j;
-      const float2 s = *reinterpret_cast<const float2*>(rowp[n2 / 10] + n1 + 16 * n2);
+      const float2 s = *reinterpret_cast<const float2*>(sig_frame + n1 + 16 * n2 + 2 * (n2 / 10));
       x[n2] = vmul(f2{s}, mk2(c.x, c.y));
     }
     if (2 * j + 1 < 25) {
       const int n2 = 2 * j + 1;
-      const float2 s = *reinterpret_cast<const float2*>(rowp[n2 / 10] + n1 + 16 * n2);
+      const float2 s = *reinterpret_cast<const float2*>(sig_frame + n1 + 16 * n2 + 2 * (n2 / 10));
       x[n2] = vmul(f2{s}, mk2(c.z, c.w));
     }
   }
-}
-// zcol = z + frame
-WFE_DEV void stage1_compute_store(const f2 (&x)[25], const float4* __restrict__ cst, int n1, float* __restrict__ zcol) {
   cx<f2> y[13];
   dft25_real<f2>(x, y);
   zcol[z_index(0, n1, 0)] = y[0].r.v.x;
@@ -327,14 +317,6 @@ WFE_DEV void stage1_compute_store(const f2 (&x)[25], const float4* __restrict__ 
     zcol[z_index(z_plane(k2, 1), n1, 0)] = zz.i.v.x;
     zcol[z_index(z_plane(k2, 1), n1 + 1, 0)] = zz.i.v.y;
   }
-}
-// sig: the tile's signal buffer; f: frame (lane)
-WFE_DEV void stage1_pair(const float* __restrict__ sig, int f, const float4* __restrict__ cst, int n1,
-                         float* __restrict__ zcol) {
-  f2 x[25];
-  const float* const rowp[3] = {sig_row_ptr(sig, f, 0), sig_row_ptr(sig, f, 1), sig_row_ptr(sig, f, 2)};
-  stage1_load(rowp, cst, n1, x);
-  stage1_compute_store(x, cst, n1, zcol);
 }
 
 // ---- stage 2 for one (frame, k2 pair (a, a+1)), a odd in 1..11: DFT-16 over n1, power -------------------

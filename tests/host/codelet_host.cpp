@@ -17,14 +17,14 @@ void codelet_tile_power(const float* sig, float* power) {
     fill_stage1_consts(cst);
     init = true;
   }
-  alignas(16) static float skew[5360 + kSigSkew * (5360 / kSigBlock + 1) + 8];
+  alignas(16) static float skew[5360 + 2 * (5360 / 160) + 8];
   static float zbuf[kZPlanes * 16 * kTileF];
   static float pbuf[kBins * kPStride];
   memset(pbuf, 0, sizeof(pbuf));
-  for (int i = 0; i < 5360; ++i) skew[sig_pos(i)] = sig[i];
+  for (int i = 0; i < 5360; ++i) skew[i + 2 * (i / kHop)] = sig[i];
   for (int lane = 0; lane < 32; ++lane)
     for (int w = 0; w < 8; ++w)
-      stage1_pair(skew, lane, reinterpret_cast<const float4*>(cst) + w * kS1ConstVec, 2 * w, zbuf + lane);
+      stage1_pair(skew + (kHop + 2) * lane, reinterpret_cast<const float4*>(cst) + w * kS1ConstVec, 2 * w, zbuf + lane);
   for (int lane = 0; lane < 32; ++lane) {
     f2 pw[16];
     for (int a = 1; a < 13; a += 2) {
