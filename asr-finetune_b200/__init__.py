@@ -10,9 +10,11 @@ from . import _lib
 from .collator import (DataCollatorSpeechSeq2SeqWithPadding, StreamingFrontendCollator, collate_parquet,
                        labels_fixed_length)
 from .feature_extraction import BatchFeature, WhisperFeatureExtractor, slaney_mel_filter_bank
+from .materialize import iter_parquet, materialize_batch, record_to_arrays, sample_records, to_host_batch, write_parquet
 from .sharding import rank_shard, shard_batches
 
 __all__ = ["WhisperFeatureExtractor", "DataCollatorSpeechSeq2SeqWithPadding", "StreamingFrontendCollator",
            "collate_parquet", "labels_fixed_length", "BatchFeature", "slaney_mel_filter_bank", "rank_shard",
-           "shard_batches", "_lib"]
+           "shard_batches", "materialize_batch", "write_parquet", "iter_parquet", "sample_records", "record_to_arrays",
+           "to_host_batch", "_lib"]
 __version__ = "0.1.0"

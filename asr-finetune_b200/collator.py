@@ -196,7 +196,8 @@ def collate_parquet(batch, device: Optional[torch.device] = None) -> dict:
     dev = device or torch.device("cuda", torch.cuda.current_device())
     f = torch.empty((len(feats),) + feats[0].shape, dtype=torch.float32, pin_memory=True)
     lab = torch.empty((len(labels),) + labels[0].shape, dtype=torch.int64, pin_memory=True)
-    for i, (a, b) in enumerate(zip(feats, labels)):
-        f[i].copy_(torch.from_numpy(a))
-        lab[i].copy_(torch.from_numpy(b))
+    fn, ln = f.numpy(), lab.numpy()
+    for i, (a, b) in enumerate(zip(feats, labels)):  # (Parquet readers hand out read-only arrays: copy through numpy)
+        np.copyto(fn[i], a)
+        np.copyto(ln[i], b)
     return {"input_features": f.to(dev, non_blocking=True), "labels": lab.to(dev, non_blocking=True)}

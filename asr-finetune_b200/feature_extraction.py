@@ -297,7 +297,9 @@ class WhisperFeatureExtractor:
                            f"`{self.__class__.__name__}()`. Failing to do so can result in silent errors that might "
                            "be hard to debug.")
         if self.dither != 0.0:
-            raise NotImplementedError("dither != 0 is not supported by the sm_100a frontend")
+            # HF adds `dither * randn` to the PADDED waveform (HF ...:146-147): the padded batch is built on the device
+            return self._call_dithered(raw_speech, truncation, pad_to_multiple_of, return_tensors,
+                                       return_attention_mask, padding, max_length, do_normalize, output_device)
 
         # ---- batched / unbatched normalisation (HF ...:274-290) ----
         if torch.is_tensor(raw_speech):
@@ -384,6 +386,53 @@ class WhisperFeatureExtractor:
             feats, mask = self.logmel_device(pcm, d_meta[:B], B, n_samples=n_samples, do_normalize=norm,
                                              return_attention_mask=want_mask, lengths=d_meta[B:])
         keep = output_device is not None and str(output_device).startswith("cuda") or (output_device is None and clips[0].is_cuda)
+        if not keep:
+            feats = feats.cpu()
+            mask = mask.cpu() if mask is not None else None
+        as_pt = keep or return_tensors in ("pt", "torch")
+        data = {"input_features": feats if as_pt else feats.numpy()}
+        if want_mask:
+            data["attention_mask"] = mask if as_pt else mask.numpy()
+        return BatchFeature(data)
+
+    def _call_dithered(self, raw_speech, truncation, pad_to_multiple_of, return_tensors, return_attention_mask, padding,
+                       max_length, do_normalize, output_device):
+        """`dither != 0`: zero-pad to the target length on the device, add `dither * N(0, 1)` to every sample of the
+        padded buffer (padding included, as HF does), then run the kernels on the full-length clips.  The noise comes
+        from torch's CUDA generator, so results are reproducible under `torch.manual_seed` but not bit-equal to HF."""
+        if torch.is_tensor(raw_speech):
+            seqs = [raw_speech] if raw_speech.dim() == 1 else list(raw_speech)
+        elif isinstance(raw_speech, np.ndarray) and raw_speech.ndim > 1:
+            seqs = list(raw_speech)
+        elif isinstance(raw_speech, (list, tuple)) and len(raw_speech) and isinstance(
+                raw_speech[0], (np.ndarray, tuple, list, torch.Tensor)):
+            seqs = list(raw_speech)
+        else:
+            seqs = [raw_speech]
+        dev = self.cuda_device()
+        clips = [(c if torch.is_tensor(c) else torch.from_numpy(np.asarray(c, dtype=np.float32))).reshape(-1).to(
+            torch.float32) for c in seqs]
+        n_samples, lens = self._resolve_length([int(c.numel()) for c in clips], truncation, padding, max_length,
+                                               pad_to_multiple_of)
+        want_mask = bool(return_attention_mask if return_attention_mask is not None else self.return_attention_mask)
+        norm = bool(do_normalize) if do_normalize is not None else bool(self.do_normalize)
+        B = len(clips)
+        with torch.cuda.device(dev):
+            pcm = torch.zeros((B, n_samples), dtype=torch.float32, device=dev)
+            for i, (c, n) in enumerate(zip(clips, lens)):
+                pcm[i, :n].copy_(c[:n], non_blocking=True)
+            if norm:  # zero-mean / unit-variance over the REAL samples comes before the dither (HF ...:306-312)
+                for i, n in enumerate(lens):
+                    v = pcm[i, :n]
+                    pcm[i, :n] = (v - v.mean()) / torch.sqrt(v.var(unbiased=False) + 1e-7)
+            pcm.add_(torch.randn(pcm.shape, dtype=pcm.dtype, device=dev), alpha=float(self.dither))
+            offs = torch.arange(B + 1, dtype=torch.int64, device=dev) * n_samples
+            feats, _ = self.logmel_device(pcm.view(-1), offs, B, n_samples=n_samples)
+            mask = None
+            if want_mask:
+                t = torch.arange(n_samples // self.hop_length, device=dev) * self.hop_length
+                mask = (t[None, :] < torch.tensor(lens, device=dev)[:, None]).to(torch.int32)
+        keep = output_device is not None and str(output_device).startswith("cuda")
         if not keep:
             feats = feats.cpu()
             mask = mask.cpu() if mask is not None else None

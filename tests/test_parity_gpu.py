@@ -319,3 +319,68 @@ def test_host_entry_reports_pcie_bytes(fe128):
     up, down = fe128.last_transfer_bytes
     assert up == sum(len(c) for c in clips) * 4 + 2 * 5 * 8  # ragged: only real samples cross PCIe (+ starts, lengths)
     assert down == 5 * 128 * 3000 * 4
+
+
+def test_materialize_batch_fixed_448_and_parquet_reader_into_collate_parquet(fe80, tmp_path):
+    # ref:finetune/prepare_dataset/materialize_dataset.py:63-183 (process_batch -> Parquet) and
+    # ref:.../datasets_and_collators.py:279-294 (collate_parquet) with the arrays produced by the kernels
+    clips = [signals.noise(40 + i, 30000 + 7777 * i) for i in range(5)]
+    labels = signals.label_ids(7, 5, 5, 60)
+    batch = pkg.materialize_batch(fe80, clips, labels, idx=[10, 11, 12, 13, 14])
+    assert batch["input_features"].shape == (5, 80, 3000) and batch["input_features"].dtype == np.float32
+    assert batch["labels"].shape == (5, 448) and batch["labels"].dtype == np.int64
+    for i in range(5):
+        assert np.abs(batch["input_features"][i] - ologmel.logmel_clip(clips[i], 80, "fp64")).max() <= TOL
+        np.testing.assert_array_equal(batch["labels"][i], ocollate.labels_fixed_length(labels[i], signals.EOT, 448))
+    path = os.path.join(tmp_path, "m.parquet")
+    assert pkg.write_parquet(path, [batch]) == 5
+    rows = next(pkg.iter_parquet(path, batch_size=5))
+    out = pkg.collate_parquet(rows)
+    assert out["input_features"].is_cuda and out["labels"].is_cuda
+    assert torch.equal(out["input_features"].cpu(), torch.from_numpy(batch["input_features"]))
+    assert torch.equal(out["labels"].cpu(), torch.from_numpy(batch["labels"]))
+    # batch-longest labels (the streaming collator's choice)
+    b2 = pkg.materialize_batch(fe80, clips, labels, max_label_length=None)
+    assert b2["labels"].shape == (5, max(len(x) for x in labels))
+
+
+def test_dither_adds_noise_of_the_requested_level():
+    # HF ...feature_extraction_whisper.py:146-147: waveform += dither * randn over the PADDED waveform.  Random, so the
+    # check is statistical: a silent clip dithered at sigma has the log-mel of white noise at sigma (within 0.05 in
+    # feature units = 0.2 decades... of the mean), everywhere including the zero padding; dither=0 stays exact.
+    sigma = 1e-3
+    fe = pkg.WhisperFeatureExtractor(feature_size=80, dither=sigma)
+    torch.manual_seed(0)
+    out = fe(np.zeros(16000, np.float32), sampling_rate=16000, return_attention_mask=True)
+    feats = out.input_features[0]
+    assert feats.shape == (80, 3000) and int(out["attention_mask"].sum()) == 100
+    ref = ologmel.logmel_clip(sigma * np.random.default_rng(0).standard_normal(480000).astype(np.float32), 80, "fp64")
+    assert abs(float(feats.mean()) - float(ref.mean())) < 0.02
+    assert abs(float(feats[:, 2000:].mean()) - float(ref[:, 2000:].mean())) < 0.02  # the padding is dithered too
+    torch.manual_seed(0)
+    again = fe(np.zeros(16000, np.float32), sampling_rate=16000).input_features[0]
+    np.testing.assert_array_equal(again, feats)  # reproducible under torch.manual_seed
+    clip = signals.noise(3, 50000)
+    plain = pkg.WhisperFeatureExtractor(feature_size=80)(clip, sampling_rate=16000).input_features[0]
+    tiny = pkg.WhisperFeatureExtractor(feature_size=80, dither=1e-7)(clip, sampling_rate=16000).input_features[0]
+    assert np.abs(tiny[:, :300] - plain[:, :300]).max() < 1e-3  # a negligible dither leaves real audio unchanged
+
+
+def test_in_loop_training_consumer_tiny_whisper(fe80):
+    # the GPU collate_fn hands CUDA tensors straight to an HF-style training step; `data_collator_id`'s
+    # `.to(f"cuda:{LOCAL_RANK}")` (ref:finetune/training/trainers/utils.py:108-112) is then a no-op
+    tr = pytest.importorskip("transformers")
+    cfg = tr.WhisperConfig(vocab_size=51866, num_mel_bins=80, d_model=64, encoder_layers=1, decoder_layers=1,
+                           encoder_attention_heads=2, decoder_attention_heads=2, encoder_ffn_dim=128, decoder_ffn_dim=128,
+                           max_source_positions=1500, max_target_positions=448, decoder_start_token_id=50258,
+                           pad_token_id=50257, bos_token_id=50257, eos_token_id=50257)
+    torch.manual_seed(0)
+    model = tr.WhisperForConditionalGeneration(cfg).cuda()
+    coll = pkg.StreamingFrontendCollator(fe80)
+    batch = coll({"audio": [signals.noise(i, 16000 * (i + 2)) for i in range(4)], "labels": signals.label_ids(3, 4, 5, 20)})
+    moved = {k: v.to("cuda:0") for k, v in batch.items()}  # what data_collator_id does
+    assert all(moved[k].data_ptr() == batch[k].data_ptr() for k in batch)  # no copy: already there
+    with torch.autocast("cuda", dtype=torch.float16):
+        loss = model(input_features=batch["input_features"], labels=batch["labels"]).loss
+    loss.backward()
+    assert torch.isfinite(loss) and model.model.encoder.conv1.weight.grad is not None
