@@ -384,3 +384,65 @@ def test_in_loop_training_consumer_tiny_whisper(fe80):
         loss = model(input_features=batch["input_features"], labels=batch["labels"]).loss
     loss.backward()
     assert torch.isfinite(loss) and model.model.encoder.conv1.weight.grad is not None
+
+
+def test_config3_full_size_batch_1024_properties(fe128):
+    # BASELINE configs[2] at its full size: 1024 ragged clips (1-30 s) + labels; size-independent properties on every
+    # clip, the oracle on a few.  (~1 GB of PCM, 1.57 GB of features)
+    B = 1024
+    lens = signals.clip_lengths(1337, B)
+    dev = fe128.cuda_device()
+    starts = np.zeros(B, dtype=np.int64)
+    np.cumsum((lens[:-1] + 3) & ~3, out=starts[1:])  # 16-byte aligned clip starts, like the Python shim
+    g = torch.Generator(device=dev)
+    g.manual_seed(1337)
+    pcm = 0.1 * torch.randn(int(starts[-1] + lens[-1]), device=dev, generator=g)
+    feats, mask = fe128.logmel_device(pcm, torch.from_numpy(starts).to(dev), B, return_attention_mask=True,
+                                      lengths=torch.from_numpy(lens).to(dev))
+    assert torch.isfinite(feats).all()
+    assert torch.equal(mask.cpu(), torch.from_numpy(ologmel.frame_attention_mask(lens)))
+    gmax = feats.amax(dim=(1, 2))
+    assert bool((feats.amin(dim=(1, 2)) >= gmax - 2.0).all())  # the per-clip clamp reached every tile of every clip
+    floor = torch.maximum(gmax - 2.0, torch.full_like(gmax, -1.5))
+    t_sil = torch.from_numpy((lens + 200) // 160 + 1).to(dev)  # frames from here on see only zero padding
+    tcol = torch.arange(3000, device=dev)[None, :]
+    silent = tcol >= t_sil[:, None]
+    assert bool(((feats == floor[:, None, None]) | ~silent[:, None, :]).all())
+    for b in (0, 511, 1023):
+        clip = pcm[starts[b]:starts[b] + lens[b]].cpu().numpy()
+        assert np.abs(feats[b].cpu().numpy() - ologmel.logmel_clip(clip, 128, "fp64")).max() <= TOL, b
+    labels = signals.label_ids(1337, B, 5, 448)
+    coll = pkg.DataCollatorSpeechSeq2SeqWithPadding(processor=type("P", (), {"feature_extractor": fe128})(),
+                                                    decoder_start_token_id=signals.SOT)
+    batch = coll({"input_features": [f for f in feats[:64]], "labels": labels[:64]})  # gather kernel on 64 device matrices
+    _, l_ref = ocollate.collate_padding([np.zeros((1, 1), np.float32)] * 64, labels[:64], signals.EOT, signals.SOT)
+    assert torch.equal(batch["labels"].cpu(), torch.from_numpy(l_ref))
+    assert torch.equal(batch["input_features"], feats[:64])
+    _, lab_all = pkg.collator.collate_labels_and_features(fe128, labels, None, width=None,
+                                                          decoder_start_token_id=signals.SOT, strip_bos=True)
+    _, l_all = ocollate.collate_padding([np.zeros((1, 1), np.float32)] * B, labels, signals.EOT, signals.SOT)
+    assert torch.equal(lab_all.cpu(), torch.from_numpy(l_all))
+
+
+def test_concurrent_calls_from_two_threads_are_independent(fe80):
+    # SURVEY 8(b) threading: the extractor is called from Ray Data prefetch threads; entry points must be re-entrant
+    import threading
+
+    clips = {0: [signals.noise(70 + i, 40000 + 1111 * i) for i in range(6)],
+             1: [signals.tone(300.0 + 50 * i, 90000 - 999 * i, 0.2) for i in range(6)]}
+    want = {k: np.stack([ologmel.logmel_clip(c, 80, "fp64") for c in v]) for k, v in clips.items()}
+    got, errs = {}, []
+
+    def work(k):
+        try:
+            for _ in range(5):
+                got[k] = fe80(clips[k], sampling_rate=16000).input_features
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(k,)) for k in clips]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+    for k in clips:
+        assert np.abs(got[k] - want[k]).max() <= TOL
