@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import ctypes as C
 import itertools
+from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass, field
 from typing import Any, Callable, Iterable, Optional, Sequence
 
@@ -165,19 +166,26 @@ class StreamingFrontendCollator:
         if len(audio) == 0:
             raise RuntimeError("No valid data in batch")  # ref ...:186-187
         if "labels" in batch:
-            label_lists = [list(x) for x in batch["labels"]]
+            label_lists = [x if isinstance(x, list) else list(x) for x in batch["labels"]]
         else:
             if self.tokenizer is None:
                 raise ValueError("need `labels` or a tokenizer for `transcription`")
             label_lists = [self.tokenizer(t if isinstance(t, str) else str(t)).input_ids for t in batch["transcription"]]
         fe = self.feature_extractor
+        if self.device is not None and str(self.device) == "cpu":
+            # host tensors wanted: the audio goes through the pipelined host entry (chunked H2D / kernels / D2H on three
+            # streams, GIL released) while a worker thread packs and collates the labels
+            dev = fe.cuda_device()
+            with ThreadPoolExecutor(max_workers=1) as pool:
+                fut = pool.submit(lambda: collate_labels_and_features(fe, label_lists, None, width=None,
+                                                                      decoder_start_token_id=-1, strip_bos=False,
+                                                                      device=dev)[1].cpu())
+                feats = fe(audio, sampling_rate=fe.sampling_rate, return_tensors="pt")["input_features"]
+                return {"input_features": feats, "labels": fut.result()}
         out = fe(audio, sampling_rate=fe.sampling_rate, return_tensors="pt", output_device="cuda")
         _, labels = collate_labels_and_features(fe, label_lists, None, width=None, decoder_start_token_id=-1,
                                                 strip_bos=False, device=out["input_features"].device)
-        res = {"input_features": out["input_features"], "labels": labels}
-        if self.device is not None and str(self.device) == "cpu":
-            res = {k: v.cpu() for k, v in res.items()}
-        return res
+        return {"input_features": out["input_features"], "labels": labels}
 
 
 def labels_fixed_length(fe, id_list: Sequence[int], max_length: int = 448) -> torch.Tensor:

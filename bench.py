@@ -414,13 +414,13 @@ def run_b200(args):
     # ---- e2e: public API with pinned host buffers, H2D + kernels + D2H inside the timed region ----
     e2e_steps = args.e2e_steps or min(args.steps, 5)
 
+    host_collate = pkg.StreamingFrontendCollator(fe, device="cpu")
+
     def host_step():
-        # label half of the padding collator (H2D ids, kernel; no host sync as the labels carry no BOS to strip) is
-        # queued first so that it overlaps the blocking extractor call; its D2H read closes the step
-        lab_d = pkg.collator.collate_labels_and_features(fe, labels, None, width=None, decoder_start_token_id=-1,
-                                                         strip_bos=False)[1]
-        out = fe(host_clips, sampling_rate=16000, return_tensors="pt")  # host numpy in -> host (pinned) tensors out
-        return out["input_features"], lab_d.cpu()
+        # the reference's training collate_fn (SimpleStreamingCollator, ref ...datasets_and_collators.py:133-256) in its
+        # drop-in form: host clips + label id lists in -> host (pinned) input_features + labels out
+        out = host_collate({"audio": host_clips, "labels": labels})
+        return out["input_features"], out["labels"]
 
     for _ in range(2):
         feats_h, lab_h = host_step()
@@ -448,8 +448,9 @@ def run_b200(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, n_gpus),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "WhisperFeatureExtractor(list_of_host_clips, sampling_rate=16000) + "
-                                               "label collate, pinned host buffers, wall clock, max over ranks"},
+                    "steps": e2e_steps, "api": "StreamingFrontendCollator(fe, device='cpu')({'audio': host_clips, 'labels': id_lists}) = "
+                                               "WhisperFeatureExtractor(list_of_host_clips) + label collate; pinned host "
+                                               "buffers, wall clock, max over ranks"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "wfe::logmel_kernel<float>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
