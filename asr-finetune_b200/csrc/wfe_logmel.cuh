@@ -200,22 +200,23 @@ __device__ __forceinline__ void fix_tile(float* __restrict__ out, int n_mel, int
     const size_t stride = (size_t)(n_frames >> 2);  // float4 per mel row
     float4* const base = reinterpret_cast<float4*>(out + (size_t)fx.b * n_mel * n_frames + t0) + q;
     const float4 c = make_float4(fl, fl, fl, fl);
-    for (int m0 = 4 * wi + r; m0 < n_mel; m0 += 32 * nw) {
+    constexpr int kDeep = 8;  // rows in flight per thread (16 spills the kernel out of its 128 registers: measured slower)
+    for (int m0 = 4 * wi + r; m0 < n_mel; m0 += 4 * kDeep * nw) {
       if (fx.silent) {  // (max(-10, g-8) + 4) / 4 everywhere
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < kDeep; ++j) {
           const int m = m0 + 4 * nw * j;
           if (m < n_mel) base[(size_t)m * stride] = c;
         }
       } else {
-        float4 v[8];
+        float4 v[kDeep];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < kDeep; ++j) {
           const int m = m0 + 4 * nw * j;
           v[j] = m < n_mel ? __ldcg(base + (size_t)m * stride) : make_float4(3.0e38f, 3.0e38f, 3.0e38f, 3.0e38f);
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < kDeep; ++j) {
           const int m = m0 + 4 * nw * j;
           // (-inf, the log of a zero mel power, is below every floor)
           if (fminf(fminf(v[j].x, v[j].y), fminf(v[j].z, v[j].w)) < fl)
@@ -378,7 +379,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
   __shared__ TileDesc s_desc[2];         // descriptor of tile k lives in slot k & 1
   __shared__ FixEntry s_fix[1];          // kernel tail only: the entry all warps work on
   __shared__ int2 s_pend_bt[kRing];      // (clip, tile | kSilentBit: tile lies in the zero padding, not yet written)
-  __shared__ float s_pend_min[kRing];    // tile minimum of y (-inf when a mel power is 0)
+  __shared__ float2 s_pend_mm[kRing];    // tile (minimum, maximum) of y (minimum -inf when a mel power is 0)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool sched = tid == 7 * 32;  // lane 0 of warp 7: tile scheduler; the whole of warp 7 keeps the clamp's books
@@ -486,12 +487,12 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
         // without ever waiting, so this wait terminates
         if (ring_count == kRing) {
           const int2 bt = s_pend_bt[ring_head];
-          const float pm = s_pend_min[ring_head];
+          const float2 pm = s_pend_mm[ring_head];
           ring_head = (ring_head + 1) & (kRing - 1);
           --ring_count;
           const float fl = wait_clip_floor(p, bt.x, lane);
-          if (pm < fl) {
-            const FixEntry fx{bt.x, bt.y & ~kSilentBit, fl, (bt.y & kSilentBit) != 0};
+          if (pm.x < fl) {
+            const FixEntry fx{bt.x, bt.y & ~kSilentBit, fl, (bt.y & kSilentBit) != 0 || pm.y <= fl};
             fix_tile(p.out, p.n_mel, p.n_frames, fx, 0, 1, lane);
           }
         }
@@ -499,7 +500,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
           st_relaxed_u32(p.tile_key + (size_t)prev_b * p.ntiles + prev_tile, f2key(mx));
           const int slot = (ring_head + ring_count) & (kRing - 1);
           s_pend_bt[slot] = make_int2(prev_b, prev_tile | (prev_silent ? kSilentBit : 0));
-          s_pend_min[slot] = mn;
+          s_pend_mm[slot] = make_float2(mn, mx);
         }
         ++ring_count;
       }
@@ -517,17 +518,18 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
         if (chk0 >= 0 && !z0) {
           const float floor_y = fmaxf(key2f(m0) - 2.0f, -1.5f);
           const int2 bt = s_pend_bt[ring_head];
-          const float pm = s_pend_min[ring_head];
+          const float2 pm = s_pend_mm[ring_head];
           ring_head = (ring_head + 1) & (kRing - 1);
           --ring_count;
-          if (pm < floor_y) fxa = FixEntry{bt.x, bt.y & ~kSilentBit, floor_y, (bt.y & kSilentBit) != 0};
+          // a tile wholly at or below the floor becomes the constant without being read back
+          if (pm.x < floor_y) fxa = FixEntry{bt.x, bt.y & ~kSilentBit, floor_y, (bt.y & kSilentBit) != 0 || pm.y <= floor_y};
           if (chk1 >= 0 && !z1) {
             const float floor1 = fmaxf(key2f(m1) - 2.0f, -1.5f);
             const int2 bt1 = s_pend_bt[ring_head];
-            const float pm1 = s_pend_min[ring_head];
+            const float2 pm1 = s_pend_mm[ring_head];
             ring_head = (ring_head + 1) & (kRing - 1);
             --ring_count;
-            if (pm1 < floor1) fxb = FixEntry{bt1.x, bt1.y & ~kSilentBit, floor1, (bt1.y & kSilentBit) != 0};
+            if (pm1.x < floor1) fxb = FixEntry{bt1.x, bt1.y & ~kSilentBit, floor1, (bt1.y & kSilentBit) != 0 || pm1.y <= floor1};
           }
         }
       }
@@ -653,7 +655,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
       if (lane == 0) {
         const int slot = (ring_head + ring_count) & (kRing - 1);
         s_pend_bt[slot] = make_int2(prev_b, prev_tile | (prev_silent ? kSilentBit : 0));
-        s_pend_min[slot] = mn;
+        s_pend_mm[slot] = make_float2(mn, mx);
       }
       ++ring_count;
     } else {  // ring full (see above): fix this one with warp 7 alone once its clip completes
@@ -670,11 +672,12 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
       __syncwarp();  // the ring entries written by lane 0 are visible to the warp
       if (ring_count > 0) {
         const int2 bt = s_pend_bt[ring_head];
-        const float pm = s_pend_min[ring_head];
+        const float2 pm = s_pend_mm[ring_head];
         ring_head = (ring_head + 1) & (kRing - 1);
         --ring_count;
         const float fl = wait_clip_floor(p, bt.x, lane);
-        if (lane == 0) s_fix[0] = FixEntry{bt.x, pm < fl ? (bt.y & ~kSilentBit) : -1, fl, (bt.y & kSilentBit) != 0};
+        if (lane == 0)
+          s_fix[0] = FixEntry{bt.x, pm.x < fl ? (bt.y & ~kSilentBit) : -1, fl, (bt.y & kSilentBit) != 0 || pm.y <= fl};
       } else if (lane == 0) {
         s_fix[0].tile = -2;  // -2: ring empty
       }
