@@ -420,13 +420,13 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
     float* const sig = sigbuf + (it & 1) * kSigBuf;
 
     WFE_TRACE(0);
-    // ---- top: start the NEXT tile's loads, then make sure this tile's signal has landed ----
+    // ---- top: make sure this tile's signal has landed, then start the NEXT tile's loads.  The prefetch is issued AFTER
+    //      the barrier: BAR.SYNC drains a warp's pending shared-memory writes, in-flight LDGSTS included, so a prefetch
+    //      issued just before S1 was waited for in full there (~2500 cycles per tile).  Measured alternatives: issued
+    //      by warp 7 alone behind stages 2-3 (no barrier ever waits: +2 % on noise, -6 % when that warp also has a clamp
+    //      fix-up per tile) or by warps 0..6 after S3 (-2 %) ----
     uint32_t idB = 0;
     if (sched) idB = atomicAdd(p.tile_counter, 1u);  // id of tile it+2, first used in this tile's stage 2
-    if (nxt.b >= 0 && nxt.mode == kModeAsync)
-      prefetch_signal(sigbuf + ((it + 1) & 1) * kSigBuf,
-                      reinterpret_cast<const float*>(p.pcm) + nxt.off + nxt.tile * kTileF * kHop - kNFft / 2, tid);
-    cp_async_commit();
     if (cur.mode == kModeSync) {
       const T* pcm = reinterpret_cast<const T*>(p.pcm) + cur.off;
       if (p.norm != nullptr) {
@@ -437,10 +437,14 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
       }
     }
     if (p.mask != nullptr && tid < nvalid) p.mask[(size_t)b * p.n_frames + t0 + tid] = ((t0 + tid) * kHop < len) ? 1 : 0;
-    cp_async_wait<1>();  // everything but the group just committed (= this tile's signal) is complete
+    cp_async_wait<0>();  // this tile's signal (the group committed during the previous tile) is complete
     WFE_TRACE(1);
     __syncthreads();     // S1: signal visible to all warps
     WFE_TRACE(2);
+    if (nxt.b >= 0 && nxt.mode == kModeAsync)  // the other buffer was last read in stage 1 of the previous tile
+      prefetch_signal(sigbuf + ((it + 1) & 1) * kSigBuf,
+                      reinterpret_cast<const float*>(p.pcm) + nxt.off + nxt.tile * kTileF * kHop - kNFft / 2, tid);
+    cp_async_commit();
 
     uint32_t rmax = 0u, rmin = 0x7f800000u;  // bit patterns of the largest / smallest mel power (identity: 0, +inf)
     if (!silent) {
