@@ -60,3 +60,22 @@ def test_logmel_matches_the_installed_extractor_on_random_clips(ref_env, n, seed
     ref = fe(clip, sampling_rate=16000).input_features[0]
     out = ologmel.logmel_clip(clip, 80, "fp64")
     assert np.abs(out - ref).max() <= 1e-3
+
+
+def test_padding_variants_of_the_installed_extractor_match_the_oracle(ref_env):
+    # `padding="longest"`, `max_length=`, `pad_to_multiple_of=` change the sample count the STFT runs on; the oracle takes
+    # it as `n_samples` (the GPU suite checks the CUDA path against the oracle with the same values)
+    _, fe = ref_env
+    clips = [signals.noise(1, 32000), signals.noise(2, 16000)]
+    o = fe(clips, sampling_rate=16000, padding="longest", return_attention_mask=True)
+    f = np.asarray(o["input_features"])
+    assert f.shape == (2, 80, 200)
+    np.testing.assert_array_equal(np.asarray(o["attention_mask"]), ologmel.frame_attention_mask([32000, 16000], 32000))
+    for i, c in enumerate(clips):
+        assert np.abs(f[i] - ologmel.logmel_clip(c, 80, "fp64", n_samples=32000)).max() <= 1e-5
+    f = np.asarray(fe(clips, sampling_rate=16000, padding="max_length", max_length=160000)["input_features"])
+    assert f.shape == (2, 80, 1000)
+    assert np.abs(f[0] - ologmel.logmel_clip(clips[0], 80, "fp64", n_samples=160000)).max() <= 1e-5
+    f = np.asarray(fe(clips, sampling_rate=16000, padding="longest", pad_to_multiple_of=48000)["input_features"])
+    assert f.shape == (2, 80, 300)
+    assert np.abs(f[1] - ologmel.logmel_clip(clips[1], 80, "fp64", n_samples=48000)).max() <= 1e-5

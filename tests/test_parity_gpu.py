@@ -446,3 +446,39 @@ def test_concurrent_calls_from_two_threads_are_independent(fe80):
     assert not errs, errs
     for k in clips:
         assert np.abs(got[k] - want[k]).max() <= TOL
+
+
+def test_padding_variants_and_input_containers(fe80):
+    # a2 / a3 / f-4: `padding="longest"`, `max_length`, `pad_to_multiple_of` (the oracle's n_samples is pinned to the
+    # installed extractor for these in tests/test_oracle_live_reference_cpu.py), int16 and torch inputs
+    clips = [signals.noise(1, 32000), signals.noise(2, 16000)]
+    o = fe80(clips, sampling_rate=16000, padding="longest", return_attention_mask=True)
+    assert o["input_features"].shape == (2, 80, 200) and o["input_features"].dtype == np.float32
+    np.testing.assert_array_equal(o["attention_mask"], ologmel.frame_attention_mask([32000, 16000], 32000))
+    for i, c in enumerate(clips):
+        assert np.abs(o["input_features"][i] - ologmel.logmel_clip(c, 80, "fp64", n_samples=32000)).max() <= TOL
+    f = fe80(clips, sampling_rate=16000, padding="max_length", max_length=160000)["input_features"]
+    assert f.shape == (2, 80, 1000)
+    assert np.abs(f[0] - ologmel.logmel_clip(clips[0], 80, "fp64", n_samples=160000)).max() <= TOL
+    f = fe80(clips, sampling_rate=16000, padding="longest", pad_to_multiple_of=48000)["input_features"]
+    assert f.shape == (2, 80, 300)
+    assert np.abs(f[1] - ologmel.logmel_clip(clips[1], 80, "fp64", n_samples=48000)).max() <= TOL
+    # int16 host input = the same integers as float32 (HF casts, it does not rescale)
+    q = np.clip(np.round(clips[0] * 32768.0), -32768, 32767).astype(np.int16)
+    a = fe80(q, sampling_rate=16000).input_features[0]
+    b = fe80(q.astype(np.float32), sampling_rate=16000).input_features[0]
+    assert np.abs(a - b).max() <= 1e-5
+    # CUDA tensor in -> CUDA tensors out (no host round trip); numpy in + output_device="cuda" likewise
+    t = torch.from_numpy(clips[0]).cuda()
+    oc = fe80(t, sampling_rate=16000, return_attention_mask=True)
+    assert oc["input_features"].is_cuda and oc["attention_mask"].is_cuda
+    ref = ologmel.logmel_clip(clips[0], 80, "fp64")
+    assert np.abs(oc["input_features"][0].cpu().numpy() - ref).max() <= TOL
+    od = fe80(clips, sampling_rate=16000, output_device="cuda")
+    assert od["input_features"].is_cuda and tuple(od["input_features"].shape) == (2, 80, 3000)
+    # batched do_normalize with the mask (HF ...:306-312): zero-mean / unit-variance over the real samples only
+    on = fe80(clips, sampling_rate=16000, do_normalize=True, return_attention_mask=True)
+    for i, c in enumerate(clips):
+        padded, _ = ologmel.pad_or_truncate(c)
+        refn = ologmel.logmel_clip(ologmel.zero_mean_unit_var(padded, len(c)), 80, "fp64")
+        assert np.abs(on["input_features"][i] - refn).max() <= TOL
