@@ -7,12 +7,14 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("WFE_LIB_OVERRIDE") or os.path.join(_HERE, "libwfe.so")  # override: timing what-if builds
 
-WFE_PCM_F32, WFE_PCM_I16 = 0, 1
+WFE_PCM_F32, WFE_PCM_I16, WFE_PCM_F16 = 0, 1, 2
+WFE_OUT_F32, WFE_OUT_F16, WFE_OUT_BF16 = 0, 1, 2
 
 # every symbol include/wfe.h declares (tests/test_abi_cpu.py checks the library exports each one)
 SYMBOLS = [
     "wfe_create", "wfe_destroy", "wfe_last_error", "wfe_abi_version", "wfe_launch_count",
     "wfe_logmel_scratch_bytes", "wfe_n_frames", "wfe_logmel", "wfe_clip_stats", "wfe_collate", "wfe_extract_host",
+    "wfe_logmel_ex", "wfe_extract_host_ex", "wfe_uses_tensor_cores", "wfe_debug_scratch_error",
 ]
 
 
@@ -55,6 +57,15 @@ def load() -> C.CDLL:
     lib.wfe_n_frames.restype = i32
     lib.wfe_logmel.argtypes = [vp, vp, i32, f32, vp, vp, i32, vp, vp, vp, vp, vp]
     lib.wfe_logmel.restype = C.c_int
+    lib.wfe_logmel_ex.argtypes = [vp, vp, i32, f32, vp, vp, i32, vp, vp, i32, vp, vp, vp]
+    lib.wfe_logmel_ex.restype = C.c_int
+    lib.wfe_uses_tensor_cores.argtypes = [vp]
+    lib.wfe_uses_tensor_cores.restype = i32
+    lib.wfe_debug_scratch_error.argtypes = [vp, vp, i32]
+    lib.wfe_debug_scratch_error.restype = i32
+    lib.wfe_extract_host_ex.argtypes = [vp, vp, vp, i32, i32, f32, i32, vp, i32, vp, C.POINTER(C.c_uint64),
+                                        C.POINTER(C.c_uint64)]
+    lib.wfe_extract_host_ex.restype = C.c_int
     lib.wfe_clip_stats.argtypes = [vp, vp, i32, f32, vp, vp, i32, vp, vp]
     lib.wfe_clip_stats.restype = C.c_int
     lib.wfe_collate.argtypes = [vp, vp, vp, i32, i32, i64, i64, vp, vp, vp, i64, vp, vp]

@@ -14,6 +14,16 @@
 #include "../../include/wfe.h"
 #include "wfe_collate.cuh"
 #include "wfe_logmel.cuh"
+#include "wfe_logmel_tc.cuh"
+
+#define WFE_TC_GEN_HOST_TABLES 1
+#define WFE_TC_GEN_NMEL 80
+#include "wfe_tc_epilogue_gen.inc"
+#undef WFE_TC_GEN_NMEL
+#define WFE_TC_GEN_NMEL 128
+#include "wfe_tc_epilogue_gen.inc"
+#undef WFE_TC_GEN_NMEL
+#undef WFE_TC_GEN_HOST_TABLES
 
 namespace {
 
@@ -54,20 +64,21 @@ struct HostSlot {
   bool busy = false;
   // staging
   void* h_in = nullptr;      // pinned, chunk * n_samples * 4 B
-  float* h_out = nullptr;    // pinned, chunk * n_mel * n_frames floats
+  void* h_out = nullptr;     // pinned, chunk * n_mel * n_frames * 4 B
   int32_t* h_mask = nullptr;
   int64_t* h_off = nullptr;  // pinned, 2 * chunk: clip starts (16-byte aligned), then clip lengths
   void* d_in = nullptr;
-  float* d_out = nullptr;
+  void* d_out = nullptr;
   int32_t* d_mask = nullptr;
   int64_t* d_off = nullptr;
   void* d_scratch = nullptr;
   float* d_stats = nullptr;
   int64_t* d_len = nullptr;
   // pending finalisation (pageable destination)
-  float* user_out = nullptr;
+  void* user_out = nullptr;
   int32_t* user_mask = nullptr;
   int pending_clips = 0;
+  size_t pending_out_bytes = 0;
 };
 
 }  // namespace
@@ -76,7 +87,11 @@ struct wfe_handle {
   wfe_config cfg;
   int n_frames = 0, ntiles = 0, n_groups = 0, n_rows = 0, sm_count = 0;
   int mel_wrange[wfe::kMelWarps + 1] = {0};
-  int ctas_per_sm[2] = {0, 0};   // resident CTAs of logmel_kernel<float>, <int16_t>
+  int ctas_per_sm[3] = {0, 0, 0};  // resident CTAs of logmel_kernel<float>, <int16_t>, <__half> (set in wfe_create)
+  bool tc_ok = false;                  // the tcgen05 kernel applies (n_samples = 480000, baked slaney filter bank)
+  uint4* d_tc_b = nullptr;             // DFT-100 operand, fp16 hi / lo, canonical UMMA layout
+  float4* d_tc_tw = nullptr;           // W400^(n1 k2) twiddles of the epilogue
+  float* d_tc_win = nullptr;           // [400] periodic Hann
   float4* d_s1_consts = nullptr;       // [8][25]
   float4* d_mel_tab = nullptr;           // [n_rows][2 halves]
   wfe::MelGroup* d_mel_groups = nullptr; // [n_groups]
@@ -89,16 +104,34 @@ struct wfe_handle {
 namespace {
 
 size_t scratch_bytes(const wfe_handle* h, int batch) {
-  // tile_key[B][ntiles] (one word per tile, zero = not published yet), tile_counter (+ pad to 16 B)
+  // tile_key[B][ntiles] (one word per tile, zero = not published yet), tile_counter, error word (+ pad to 16 B)
   return ((size_t)batch * h->ntiles + 4) * sizeof(uint32_t);
 }
 
 template <typename T>
-int launch_logmel(wfe_handle* h, const void* pcm, float scale, const int64_t* offsets, const int64_t* lengths, int batch,
-                  const float* norm, float* out, int32_t* mask, void* scratch, cudaStream_t st) {
+int prepare_cc_kernel(wfe_handle* h, int which) {
+  // opt in to > 48 KB dynamic shared memory (the attribute is per function, shared by every handle: set it to the
+  // most any filter bank can need) and size the persistent grid from the real occupancy
+  WFE_CUDA(cudaFuncSetAttribute(wfe::logmel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)wfe::logmel_smem_bytes(wfe::kMaxMelRows)));
+  WFE_CUDA(cudaFuncSetAttribute(wfe::logmel_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                cudaSharedmemCarveoutMaxShared));
+  int n = 0;
+  WFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, wfe::logmel_kernel<T>, wfe::kThreads,
+                                                         wfe::logmel_smem_bytes(h->n_rows)));
+  if (n < 1) return fail(WFE_ERR_CUDA, "logmel kernel does not fit on an SM");
+  h->ctas_per_sm[which] = n;
+  return WFE_OK;
+}
+
+// CUDA-core kernel: any geometry, any banded filter bank, fp32 output
+template <typename T>
+int launch_cc(wfe_handle* h, const void* pcm, float scale, const int64_t* offsets, const int64_t* lengths, int batch,
+              const float* norm, float* out, int32_t* mask, void* scratch, cudaStream_t st) {
   static_assert(sizeof(T) == 2 || sizeof(T) == 4, "pcm dtype");
   const long long total = (long long)batch * h->ntiles;
   if (total > 0x7fffffffLL) return fail(WFE_ERR_INVALID, "batch too large for one launch");
+  if ((reinterpret_cast<uintptr_t>(out) & 7u) != 0) return fail(WFE_ERR_INVALID, "out must be 8-byte aligned");
   wfe::LogmelParams p;
   p.pcm = pcm;
   p.offsets = offsets;
@@ -106,7 +139,6 @@ int launch_logmel(wfe_handle* h, const void* pcm, float scale, const int64_t* of
   p.norm = reinterpret_cast<const float2*>(norm);
   p.out = out;
   p.mask = mask;
-  if ((reinterpret_cast<uintptr_t>(scratch) & 3u) != 0) return fail(WFE_ERR_INVALID, "scratch must be 4-byte aligned");
   p.tile_key = reinterpret_cast<uint32_t*>(scratch);
   p.tile_counter = p.tile_key + (size_t)batch * h->ntiles;
   p.s1_consts = h->d_s1_consts;
@@ -123,25 +155,120 @@ int launch_logmel(wfe_handle* h, const void* pcm, float scale, const int64_t* of
   p.total_tiles = (uint32_t)total;
   WFE_CUDA(cudaMemsetAsync(scratch, 0, scratch_bytes(h, batch), st));
   const size_t smem = wfe::logmel_smem_bytes(h->n_rows);
-  const int which = sizeof(T) == 4 ? 0 : 1;
-  if (h->ctas_per_sm[which] == 0) {
-    // opt in to > 48 KB dynamic shared memory (the attribute is per function, shared by every handle: set it to the
-    // most any filter bank can need) and size the persistent grid from the real occupancy
-    WFE_CUDA(cudaFuncSetAttribute(wfe::logmel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)wfe::logmel_smem_bytes(wfe::kMaxMelRows)));
-    WFE_CUDA(cudaFuncSetAttribute(wfe::logmel_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                  cudaSharedmemCarveoutMaxShared));
-    int n = 0;
-    WFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, wfe::logmel_kernel<T>, wfe::kThreads, smem));
-    if (n < 1) return fail(WFE_ERR_CUDA, "logmel kernel does not fit on an SM");
-    h->ctas_per_sm[which] = n;
-  }
+  const int which = std::is_same<T, float>::value ? 0 : (std::is_same<T, int16_t>::value ? 1 : 2);
   long long grid = (long long)h->sm_count * h->ctas_per_sm[which];
   if (grid > total) grid = total;
   wfe::logmel_kernel<T><<<(unsigned)grid, wfe::kThreads, smem, st>>>(p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   WFE_CUDA(cudaGetLastError());
   return WFE_OK;
+}
+
+bool tc_disabled_by_env() {
+  const char* e = getenv("WFE_DISABLE_TC");
+  return e != nullptr && e[0] != 0 && e[0] != '0';
+}
+
+// tensor-core kernel: n_samples = 480000, baked filter bank; any PCM dtype, any output dtype
+template <typename OutT, int kNMel>
+int launch_tc(wfe_handle* h, const void* pcm, int pcm_dtype, float scale, const int64_t* offsets, const int64_t* lengths,
+              int batch, const float* norm, void* out, int32_t* mask, void* scratch, cudaStream_t st) {
+  const long long total = (long long)batch * wfe::tc::kNTiles;
+  if (total > 0x7fffffffLL) return fail(WFE_ERR_INVALID, "batch too large for one launch");
+  wfe::tc::TcParams p;
+  p.pcm = pcm;
+  p.offsets = offsets;
+  p.lengths = lengths;
+  p.norm = reinterpret_cast<const float2*>(norm);
+  p.out = out;
+  p.mask = mask;
+  p.tile_key = reinterpret_cast<uint32_t*>(scratch);
+  p.b_mat = h->d_tc_b;
+  p.tw = h->d_tc_tw;
+  p.win = h->d_tc_win;
+  p.pcm_scale = scale;
+  p.pcm_dtype = pcm_dtype;
+  p.n_mel = kNMel;
+  p.total_tiles = (uint32_t)total;
+  uint32_t* err_flag = p.tile_key + (size_t)batch * h->ntiles + 1;
+  WFE_CUDA(cudaMemsetAsync(scratch, 0, scratch_bytes(h, batch), st));
+  long long grid = h->sm_count;
+  if (grid > total) grid = total;
+  wfe::tc::logmel_tc_kernel<OutT, kNMel><<<(unsigned)grid, wfe::tc::kThreads, wfe::tc::kSmemBytes, st>>>(p, err_flag);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  WFE_CUDA(cudaGetLastError());
+  return WFE_OK;
+}
+
+template <typename OutT>
+__global__ void cast_kernel(const float* __restrict__ src, OutT* __restrict__ dst, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = wfe::tc::to_out<OutT>(src[i]);
+}
+
+template <typename OutT>
+int prepare_tc_kernels() {
+  WFE_CUDA(cudaFuncSetAttribute(wfe::tc::logmel_tc_kernel<OutT, 80>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)wfe::tc::kSmemBytes));
+  WFE_CUDA(cudaFuncSetAttribute(wfe::tc::logmel_tc_kernel<OutT, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)wfe::tc::kSmemBytes));
+  return WFE_OK;
+}
+
+int logmel_dispatch(wfe_handle* h, const void* pcm, int pcm_dtype, float scale, const int64_t* offsets,
+                    const int64_t* lengths, int batch, const float* norm, void* out, int out_dtype, int32_t* mask,
+                    void* scratch, cudaStream_t st) {
+  if (pcm_dtype != WFE_PCM_F32 && pcm_dtype != WFE_PCM_I16 && pcm_dtype != WFE_PCM_F16)
+    return fail(WFE_ERR_INVALID, "unknown pcm_dtype");
+  if (out_dtype != WFE_OUT_F32 && out_dtype != WFE_OUT_F16 && out_dtype != WFE_OUT_BF16)
+    return fail(WFE_ERR_INVALID, "unknown out_dtype");
+  if ((reinterpret_cast<uintptr_t>(scratch) & 3u) != 0) return fail(WFE_ERR_INVALID, "scratch must be 4-byte aligned");
+  if (pcm_dtype == WFE_PCM_F32) scale = 1.0f;
+  const bool tc = h->tc_ok && !tc_disabled_by_env() && (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+#ifdef WFE_EXP_MINIMAL  // experiment builds: one instantiation only (fast to compile)
+  if (tc && out_dtype == WFE_OUT_F32 && h->cfg.n_mel == 128)
+    return launch_tc<float, 128>(h, pcm, pcm_dtype, scale, offsets, lengths, batch, norm, out, mask, scratch, st);
+  if (tc) return fail(WFE_ERR_UNSUPPORTED, "minimal experiment build");
+#else
+  if (tc) {
+    const bool big = h->cfg.n_mel == 128;
+    switch (out_dtype) {
+      case WFE_OUT_F32:
+        return big ? launch_tc<float, 128>(h, pcm, pcm_dtype, scale, offsets, lengths, batch, norm, out, mask, scratch, st)
+                   : launch_tc<float, 80>(h, pcm, pcm_dtype, scale, offsets, lengths, batch, norm, out, mask, scratch, st);
+      case WFE_OUT_F16:
+        return big ? launch_tc<__half, 128>(h, pcm, pcm_dtype, scale, offsets, lengths, batch, norm, out, mask, scratch, st)
+                   : launch_tc<__half, 80>(h, pcm, pcm_dtype, scale, offsets, lengths, batch, norm, out, mask, scratch, st);
+      default:
+        return big ? launch_tc<__nv_bfloat16, 128>(h, pcm, pcm_dtype, scale, offsets, lengths, batch, norm, out, mask, scratch, st)
+                   : launch_tc<__nv_bfloat16, 80>(h, pcm, pcm_dtype, scale, offsets, lengths, batch, norm, out, mask, scratch, st);
+    }
+  }
+#endif
+  // CUDA-core kernel writes fp32; a 16-bit result takes a stream-ordered temporary and one rounding pass
+  float* out32 = reinterpret_cast<float*>(out);
+  const size_t n_out = (size_t)batch * h->cfg.n_mel * h->n_frames;
+  if (out_dtype != WFE_OUT_F32) WFE_CUDA(cudaMallocAsync((void**)&out32, n_out * sizeof(float), st));
+  int rc;
+  if (pcm_dtype == WFE_PCM_F32)
+    rc = launch_cc<float>(h, pcm, scale, offsets, lengths, batch, norm, out32, mask, scratch, st);
+  else if (pcm_dtype == WFE_PCM_I16)
+    rc = launch_cc<int16_t>(h, pcm, scale, offsets, lengths, batch, norm, out32, mask, scratch, st);
+  else
+    rc = launch_cc<__half>(h, pcm, scale, offsets, lengths, batch, norm, out32, mask, scratch, st);
+  if (out_dtype != WFE_OUT_F32) {
+    if (rc == WFE_OK) {
+      const unsigned blocks = (unsigned)std::min<size_t>((n_out + 255) / 256, (size_t)h->sm_count * 16);
+      if (out_dtype == WFE_OUT_F16)
+        cast_kernel<__half><<<blocks, 256, 0, st>>>(out32, reinterpret_cast<__half*>(out), n_out);
+      else
+        cast_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(out32, reinterpret_cast<__nv_bfloat16*>(out), n_out);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    cudaFreeAsync(out32, st);
+    if (rc == WFE_OK) WFE_CUDA(cudaGetLastError());
+  }
+  return rc;
 }
 
 int check_handle(const wfe_handle* h) {
@@ -188,11 +315,11 @@ int ensure_ring(wfe_handle* h) {
     WFE_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     WFE_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
     WFE_CUDA(cudaHostAlloc(&s.h_in, in_bytes, cudaHostAllocDefault));
-    WFE_CUDA(cudaHostAlloc((void**)&s.h_out, out_elems * sizeof(float), cudaHostAllocDefault));
+    WFE_CUDA(cudaHostAlloc(&s.h_out, out_elems * sizeof(float), cudaHostAllocDefault));
     WFE_CUDA(cudaHostAlloc((void**)&s.h_mask, c * h->n_frames * sizeof(int32_t), cudaHostAllocDefault));
     WFE_CUDA(cudaHostAlloc((void**)&s.h_off, 2 * c * sizeof(int64_t), cudaHostAllocDefault));
     WFE_CUDA(cudaMalloc(&s.d_in, in_bytes));
-    WFE_CUDA(cudaMalloc((void**)&s.d_out, out_elems * sizeof(float)));
+    WFE_CUDA(cudaMalloc(&s.d_out, out_elems * sizeof(float)));
     WFE_CUDA(cudaMalloc((void**)&s.d_mask, c * h->n_frames * sizeof(int32_t)));
     WFE_CUDA(cudaMalloc((void**)&s.d_off, 2 * c * sizeof(int64_t)));
     WFE_CUDA(cudaMalloc(&s.d_scratch, scratch_bytes(h, (int)c)));
@@ -206,11 +333,80 @@ int ensure_ring(wfe_handle* h) {
 int retire_slot(wfe_handle* h, HostSlot& s) {
   if (!s.busy) return WFE_OK;
   WFE_CUDA(cudaEventSynchronize(s.done));
-  if (s.user_out) memcpy(s.user_out, s.h_out, (size_t)s.pending_clips * h->cfg.n_mel * h->n_frames * sizeof(float));
+  if (s.user_out) memcpy(s.user_out, s.h_out, s.pending_out_bytes);
   if (s.user_mask) memcpy(s.user_mask, s.h_mask, (size_t)s.pending_clips * h->n_frames * sizeof(int32_t));
   s.user_out = nullptr;
   s.user_mask = nullptr;
   s.busy = false;
+  return WFE_OK;
+}
+
+// Tables of the tcgen05 kernel (wfe_logmel_tc.cuh).  The kernel's mel epilogue is generated code with the slaney
+// weights baked in: it only applies when the caller's filter bank has exactly those non-zeros.
+int setup_tensor_core_path(wfe_handle* h, const float* mel_filters) {
+  h->tc_ok = false;
+  const int n_mel = h->cfg.n_mel;
+  if (h->cfg.n_samples != wfe::tc::kNSamples || (n_mel != 80 && n_mel != 128)) return WFE_OK;
+  const uint32_t(*nnz)[3] = n_mel == 80 ? kTcNnz80 : kTcNnz128;
+  const size_t n_nnz = n_mel == 80 ? sizeof(kTcNnz80) / sizeof(kTcNnz80[0]) : sizeof(kTcNnz128) / sizeof(kTcNnz128[0]);
+  size_t found = 0;
+  for (int k = 0; k < wfe::kBins; ++k)
+    for (int m = 0; m < n_mel; ++m)
+      if (mel_filters[(size_t)k * n_mel + m] != 0.0f) ++found;
+  if (found != n_nnz) return WFE_OK;
+  for (size_t i = 0; i < n_nnz; ++i) {
+    uint32_t bits;
+    memcpy(&bits, &mel_filters[(size_t)nnz[i][0] * n_mel + nnz[i][1]], 4);
+    if (bits != nnz[i][2]) return WFE_OK;
+  }
+  using namespace wfe::tc;
+  const double kPi = 3.14159265358979323846;
+  // B[n][k]: n = 4 * pair + {re k2 = 2 pair, re k2 + 1, im k2, im k2 + 1}, k = n2; canonical layout [chunk][n][8 x fp16]
+  std::vector<__half> bmat((size_t)kBBytes / 2, __float2half_rn(0.0f));
+  for (int n = 0; n < kN; ++n) {
+    const int pair = n / 4, c = n % 4;
+    const int k2 = 2 * pair + (c & 1);
+    if (pair >= 26 || k2 > 50) continue;
+    for (int n2 = 0; n2 < 100; ++n2) {
+      const double ang = 2.0 * kPi * (double)((n2 * k2) % 100) / 100.0;
+      const float v = (float)(c < 2 ? cos(ang) : -sin(ang));
+      const __half hi = __float2half_rn(v);
+      const __half lo = __float2half_rn(v - __half2float(hi));
+      const size_t idx = ((size_t)(n2 / 8) * kN + n) * 8 + (n2 % 8);
+      bmat[idx] = hi;
+      bmat[(size_t)kBBytes / 4 + idx] = lo;
+    }
+  }
+  std::vector<float> tw((size_t)kTwBytes / 4);
+  for (int pair = 0; pair < 26; ++pair)
+    for (int n1 = 1; n1 <= 3; ++n1) {
+      float* t = &tw[((size_t)pair * 3 + (n1 - 1)) * 4];
+      for (int e2 = 0; e2 < 2; ++e2) {
+        const double ang = 2.0 * kPi * (double)(n1 * (2 * pair + e2)) / 400.0;
+        t[e2] = (float)cos(ang);
+        t[2 + e2] = (float)sin(ang);
+      }
+    }
+  float win[wfe::kNFft];
+  float2 unused_tw[16 * 12];
+  wfe::fill_tables(win, unused_tw);
+  if (cudaMalloc((void**)&h->d_tc_b, kBBytes) != cudaSuccess || cudaMalloc((void**)&h->d_tc_tw, kTwBytes) != cudaSuccess ||
+      cudaMalloc((void**)&h->d_tc_win, sizeof(win)) != cudaSuccess)
+    return fail(WFE_ERR_NOMEM, "cudaMalloc failed for the tensor-core tables");
+  WFE_CUDA(cudaMemcpy(h->d_tc_b, bmat.data(), kBBytes, cudaMemcpyHostToDevice));
+  WFE_CUDA(cudaMemcpy(h->d_tc_tw, tw.data(), kTwBytes, cudaMemcpyHostToDevice));
+  WFE_CUDA(cudaMemcpy(h->d_tc_win, win, sizeof(win), cudaMemcpyHostToDevice));
+#ifdef WFE_EXP_MINIMAL
+  WFE_CUDA(cudaFuncSetAttribute(wfe::tc::logmel_tc_kernel<float, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)wfe::tc::kSmemBytes));
+  int rc = WFE_OK;
+#else
+  int rc = prepare_tc_kernels<float>();
+  if (rc == WFE_OK) rc = prepare_tc_kernels<__half>();
+  if (rc == WFE_OK) rc = prepare_tc_kernels<__nv_bfloat16>();
+#endif
+  if (rc != WFE_OK) return rc;
+  h->tc_ok = true;
   return WFE_OK;
 }
 
@@ -225,6 +421,13 @@ int wfe_debug_read_trace(unsigned long long* dst, int n) {
 }
 #endif
 
+#ifdef WFE_TC_TRACE
+// timing-trace build only (not part of the shipped ABI)
+int wfe_debug_read_tc_trace(unsigned long long* dst, int n) {
+  return (int)cudaMemcpyFromSymbol(dst, wfe::tc::g_tc_trace, sizeof(unsigned long long) * n);
+}
+#endif
+
 const char* wfe_last_error(void) { return g_err.c_str(); }
 int wfe_abi_version(void) { return WFE_ABI_VERSION; }
 uint64_t wfe_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
@@ -235,8 +438,7 @@ int wfe_create(const wfe_config* cfg, const float* mel_filters, wfe_handle** out
   if (cfg->n_fft != wfe::kNFft || cfg->hop_length != wfe::kHop)
     return fail(WFE_ERR_UNSUPPORTED, "kernels are specialised for n_fft=400, hop_length=160 (every Whisper checkpoint)");
   if (cfg->n_mel < 1 || cfg->n_mel > 256) return fail(WFE_ERR_UNSUPPORTED, "n_mel must be in 1..256");
-  if (cfg->n_samples < wfe::kNFft || cfg->n_samples % wfe::kHop != 0)
-    return fail(WFE_ERR_UNSUPPORTED, "n_samples must be a multiple of 160 and >= 400");
+  if (cfg->n_samples < wfe::kNFft) return fail(WFE_ERR_UNSUPPORTED, "n_samples must be >= 400 (n_fft)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     cudaGetLastError();
@@ -360,13 +562,24 @@ int wfe_create(const wfe_config* cfg, const float* mel_filters, wfe_handle** out
     wfe_destroy(h);
     return fail(WFE_ERR_NOMEM, "cudaMalloc failed for constant tables");
   }
-  cudaMemcpy(h->d_s1_consts, s1c.data(), s1c.size() * sizeof(float), cudaMemcpyHostToDevice);
-  cudaMemcpy(h->d_mel_tab, mtab.data(), mtab.size() * sizeof(float4), cudaMemcpyHostToDevice);
-  cudaMemcpy(h->d_mel_groups, groups.data(), groups.size() * sizeof(wfe::MelGroup), cudaMemcpyHostToDevice);
-  cudaError_t e = cudaDeviceSynchronize();
+  cudaError_t e = cudaMemcpy(h->d_s1_consts, s1c.data(), s1c.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_mel_tab, mtab.data(), mtab.size() * sizeof(float4), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess)
+    e = cudaMemcpy(h->d_mel_groups, groups.data(), groups.size() * sizeof(wfe::MelGroup), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     wfe_destroy(h);
     return fail(WFE_ERR_CUDA, std::string("table upload: ") + cudaGetErrorString(e));
+  }
+  // function attributes and occupancy once, here, so that wfe_logmel is re-entrant
+  int rc = prepare_cc_kernel<float>(h, 0);
+  if (rc == WFE_OK) rc = prepare_cc_kernel<int16_t>(h, 1);
+  if (rc == WFE_OK) rc = prepare_cc_kernel<__half>(h, 2);
+  if (rc == WFE_OK) rc = setup_tensor_core_path(h, mel_filters);
+  if (rc != WFE_OK) {
+    const std::string msg = g_err;
+    wfe_destroy(h);
+    return fail(rc, msg);
   }
   *out = h;
   return WFE_OK;
@@ -379,6 +592,9 @@ void wfe_destroy(wfe_handle* h) {
   if (h->d_s1_consts) cudaFree(h->d_s1_consts);
   if (h->d_mel_tab) cudaFree(h->d_mel_tab);
   if (h->d_mel_groups) cudaFree(h->d_mel_groups);
+  if (h->d_tc_b) cudaFree(h->d_tc_b);
+  if (h->d_tc_tw) cudaFree(h->d_tc_tw);
+  if (h->d_tc_win) cudaFree(h->d_tc_win);
   delete h;
 }
 
@@ -389,9 +605,9 @@ size_t wfe_logmel_scratch_bytes(const wfe_handle* h, int32_t batch) {
 
 int32_t wfe_n_frames(const wfe_handle* h) { return h ? h->n_frames : 0; }
 
-int wfe_logmel(wfe_handle* h, const void* pcm, int32_t pcm_dtype, float pcm_scale, const int64_t* offsets,
-               const int64_t* lengths, int32_t batch, const float* norm_stats, float* out, int32_t* attn_mask,
-               void* scratch, void* stream) {
+int wfe_logmel_ex(wfe_handle* h, const void* pcm, int32_t pcm_dtype, float pcm_scale, const int64_t* offsets,
+                  const int64_t* lengths, int32_t batch, const float* norm_stats, void* out, int32_t out_dtype,
+                  int32_t* attn_mask, void* scratch, void* stream) {
   if (check_handle(h)) return WFE_ERR_INVALID;
   if (batch < 0) return fail(WFE_ERR_INVALID, "negative batch");
   if (batch == 0) return WFE_OK;
@@ -399,15 +615,26 @@ int wfe_logmel(wfe_handle* h, const void* pcm, int32_t pcm_dtype, float pcm_scal
     return fail(WFE_ERR_INVALID, "null device pointer");
   DeviceGuard guard(h->cfg.device);
   if (!guard.ok) return fail(WFE_ERR_CUDA, "cudaSetDevice failed");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  switch (pcm_dtype) {
-    case WFE_PCM_F32:
-      return launch_logmel<float>(h, pcm, 1.0f, offsets, lengths, batch, norm_stats, out, attn_mask, scratch, st);
-    case WFE_PCM_I16:
-      return launch_logmel<int16_t>(h, pcm, pcm_scale, offsets, lengths, batch, norm_stats, out, attn_mask, scratch, st);
-    default:
-      return fail(WFE_ERR_INVALID, "unknown pcm_dtype");
-  }
+  return logmel_dispatch(h, pcm, pcm_dtype, pcm_scale, offsets, lengths, batch, norm_stats, out, out_dtype, attn_mask,
+                         scratch, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int wfe_logmel(wfe_handle* h, const void* pcm, int32_t pcm_dtype, float pcm_scale, const int64_t* offsets,
+               const int64_t* lengths, int32_t batch, const float* norm_stats, float* out, int32_t* attn_mask,
+               void* scratch, void* stream) {
+  return wfe_logmel_ex(h, pcm, pcm_dtype, pcm_scale, offsets, lengths, batch, norm_stats, out, WFE_OUT_F32, attn_mask,
+                       scratch, stream);
+}
+
+int32_t wfe_uses_tensor_cores(const wfe_handle* h) { return (h != nullptr && h->tc_ok && !tc_disabled_by_env()) ? 1 : 0; }
+
+int32_t wfe_debug_scratch_error(wfe_handle* h, const void* scratch, int32_t batch) {
+  if (h == nullptr || scratch == nullptr || batch <= 0) return 0;
+  DeviceGuard guard(h->cfg.device);
+  uint32_t v = 0;
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(scratch) + (size_t)batch * h->ntiles + 1;
+  if (cudaMemcpy(&v, w, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return (int32_t)v;
 }
 
 int wfe_clip_stats(wfe_handle* h, const void* pcm, int32_t pcm_dtype, float pcm_scale, const int64_t* offsets,
@@ -423,6 +650,8 @@ int wfe_clip_stats(wfe_handle* h, const void* pcm, int32_t pcm_dtype, float pcm_
     wfe::clip_stats_kernel<float><<<batch, 512, 0, st>>>(pcm, 1.0f, offsets, lengths, h->cfg.n_samples, reinterpret_cast<float2*>(stats));
   else if (pcm_dtype == WFE_PCM_I16)
     wfe::clip_stats_kernel<int16_t><<<batch, 512, 0, st>>>(pcm, pcm_scale, offsets, lengths, h->cfg.n_samples, reinterpret_cast<float2*>(stats));
+  else if (pcm_dtype == WFE_PCM_F16)
+    wfe::clip_stats_kernel<__half><<<batch, 512, 0, st>>>(pcm, 1.0f, offsets, lengths, h->cfg.n_samples, reinterpret_cast<float2*>(stats));
   else
     return fail(WFE_ERR_INVALID, "unknown pcm_dtype");
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -456,14 +685,14 @@ int wfe_collate(wfe_handle* h, const int64_t* ids, const int64_t* offsets, int32
   const long long label_elems = (long long)batch * width;
   long long lb = (label_elems + wfe::kCollateThreads - 1) / wfe::kCollateThreads;
   if (lb < 1) lb = 1;
-  if (lb > 148 * 4) lb = 148 * 4;
+  if (lb > (long long)h->sm_count * 4) lb = (long long)h->sm_count * 4;
   p.label_blocks = (int)lb;
   // features: ~16 KB per block-iteration of 4 x 128-bit loads; aim for >= 2 waves of 148 SMs x 8 CTAs
   int per_clip = 0;
   if (feat_srcs != nullptr && feat_elems > 0) {
     long long want = (feat_elems / 4 + (long long)wfe::kCollateThreads * 4 - 1) / ((long long)wfe::kCollateThreads * 4);
     if (want < 1) want = 1;
-    long long cap = (148LL * 16 + batch - 1) / batch;
+    long long cap = ((long long)h->sm_count * 16 + batch - 1) / batch;
     if (cap < 1) cap = 1;
     per_clip = (int)(want < cap ? want : cap);
   }
@@ -475,22 +704,53 @@ int wfe_collate(wfe_handle* h, const int64_t* ids, const int64_t* offsets, int32
   return WFE_OK;
 }
 
-int wfe_extract_host(wfe_handle* h, const void* const* clips, const int64_t* lengths, int32_t batch,
-                     int32_t pcm_dtype, float pcm_scale, int32_t do_normalize, float* out, int32_t* attn_mask,
-                     uint64_t* h2d_bytes, uint64_t* d2h_bytes) {
+int wfe_extract_host_ex(wfe_handle* h, const void* const* clips, const int64_t* lengths, int32_t batch,
+                        int32_t pcm_dtype, float pcm_scale, int32_t do_normalize, void* out, int32_t out_dtype,
+                        int32_t* attn_mask, uint64_t* h2d_bytes, uint64_t* d2h_bytes) {
   if (check_handle(h)) return WFE_ERR_INVALID;
   if (batch < 0) return fail(WFE_ERR_INVALID, "negative batch");
   if (h2d_bytes) *h2d_bytes = 0;
   if (d2h_bytes) *d2h_bytes = 0;
   if (batch == 0) return WFE_OK;
   if (clips == nullptr || lengths == nullptr || out == nullptr) return fail(WFE_ERR_INVALID, "null host pointer");
-  if (pcm_dtype != WFE_PCM_F32 && pcm_dtype != WFE_PCM_I16) return fail(WFE_ERR_INVALID, "unknown pcm_dtype");
+  if (pcm_dtype != WFE_PCM_F32 && pcm_dtype != WFE_PCM_I16 && pcm_dtype != WFE_PCM_F16)
+    return fail(WFE_ERR_INVALID, "unknown pcm_dtype");
+  if (out_dtype != WFE_OUT_F32 && out_dtype != WFE_OUT_F16 && out_dtype != WFE_OUT_BF16)
+    return fail(WFE_ERR_INVALID, "unknown out_dtype");
+  // validate every clip BEFORE anything is enqueued: an early return must not leave copies in flight
+  for (int i = 0; i < batch; ++i) {
+    if (lengths[i] < 0) return fail(WFE_ERR_INVALID, "negative clip length");
+    if (lengths[i] > 0 && clips[i] == nullptr) return fail(WFE_ERR_INVALID, "null clip pointer");
+  }
   const size_t es = pcm_dtype == WFE_PCM_F32 ? 4 : 2;
+  const size_t os = out_dtype == WFE_OUT_F32 ? 4 : 2;
   std::lock_guard<std::mutex> lock(h->host_mu);
   DeviceGuard guard(h->cfg.device);
   if (!guard.ok) return fail(WFE_ERR_CUDA, "cudaSetDevice failed");
   int rc = ensure_ring(h);
-  if (rc != WFE_OK) return rc;
+  if (rc != WFE_OK) {
+    const std::string msg = g_err;
+    free_ring(h);  // partial allocations
+    return fail(rc, msg);
+  }
+  // on any failure below: wait for everything already enqueued and forget the caller's buffers, so that neither this
+  // call's copies outlive it nor the next call writes into them
+  struct RingGuard {
+    wfe_handle* h;
+    bool armed = true;
+    ~RingGuard() {
+      if (!armed) return;
+      const std::string msg = g_err;
+      for (auto& s : h->slots) {
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        s.busy = false;
+        s.user_out = nullptr;
+        s.user_mask = nullptr;
+      }
+      cudaGetLastError();
+      g_err = msg;
+    }
+  } ring_guard{h};
 
   const bool out_pinned = is_pinned_host(out);
   const bool mask_pinned = attn_mask != nullptr && is_pinned_host(attn_mask);
@@ -504,15 +764,13 @@ int wfe_extract_host(wfe_handle* h, const void* const* clips, const int64_t* len
     if (rc != WFE_OK) return rc;
     const int n = (batch - c0 < chunk) ? batch - c0 : chunk;
     // ragged pack: only min(len, n_samples) samples of each clip cross PCIe; every clip starts on a 16-byte boundary
-    // of the device buffer so that the kernel's 128-bit load path applies (starts in h_off[0..n), lengths after them)
+    // of the device buffer so that the kernels' vector / bulk-copy paths apply (starts in h_off[0..n), lengths after)
     int64_t* starts = s.h_off;
     int64_t* lens = s.h_off + chunk;
     int64_t pos = 0, payload = 0;
     for (int i = 0; i < n; ++i) {
       int64_t len = lengths[c0 + i];
-      if (len < 0) return fail(WFE_ERR_INVALID, "negative clip length");
       if (len > h->cfg.n_samples) len = h->cfg.n_samples;
-      if (len > 0 && clips[c0 + i] == nullptr) return fail(WFE_ERR_INVALID, "null clip pointer");
       starts[i] = pos;
       lens[i] = len;
       payload += len;
@@ -563,17 +821,18 @@ int wfe_extract_host(wfe_handle* h, const void* const* clips, const int64_t* len
       if (rc != WFE_OK) return rc;
       stats = s.d_stats;
     }
-    rc = wfe_logmel(h, s.d_in, pcm_dtype, pcm_scale, s.d_off, s.d_off + chunk, n, stats, s.d_out,
-                    attn_mask ? s.d_mask : nullptr, s.d_scratch, s.stream);
+    rc = wfe_logmel_ex(h, s.d_in, pcm_dtype, pcm_scale, s.d_off, s.d_off + chunk, n, stats, s.d_out, out_dtype,
+                       attn_mask ? s.d_mask : nullptr, s.d_scratch, s.stream);
     if (rc != WFE_OK) return rc;
-    float* dst = out + (size_t)c0 * clip_out;
+    char* dst = static_cast<char*>(out) + (size_t)c0 * clip_out * os;
+    s.pending_out_bytes = (size_t)n * clip_out * os;
     if (out_pinned) {
-      WFE_CUDA(cudaMemcpyAsync(dst, s.d_out, (size_t)n * clip_out * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+      WFE_CUDA(cudaMemcpyAsync(dst, s.d_out, s.pending_out_bytes, cudaMemcpyDeviceToHost, s.stream));
     } else {
-      WFE_CUDA(cudaMemcpyAsync(s.h_out, s.d_out, (size_t)n * clip_out * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+      WFE_CUDA(cudaMemcpyAsync(s.h_out, s.d_out, s.pending_out_bytes, cudaMemcpyDeviceToHost, s.stream));
       s.user_out = dst;
     }
-    down += (uint64_t)n * clip_out * sizeof(float);
+    down += (uint64_t)s.pending_out_bytes;
     if (attn_mask) {
       int32_t* mdst = attn_mask + (size_t)c0 * h->n_frames;
       if (mask_pinned) {
@@ -593,9 +852,17 @@ int wfe_extract_host(wfe_handle* h, const void* const* clips, const int64_t* len
     rc = retire_slot(h, h->slots[slot_i]);
     if (rc != WFE_OK) return rc;
   }
+  ring_guard.armed = false;
   if (h2d_bytes) *h2d_bytes = up;
   if (d2h_bytes) *d2h_bytes = down;
   return WFE_OK;
+}
+
+int wfe_extract_host(wfe_handle* h, const void* const* clips, const int64_t* lengths, int32_t batch,
+                     int32_t pcm_dtype, float pcm_scale, int32_t do_normalize, float* out, int32_t* attn_mask,
+                     uint64_t* h2d_bytes, uint64_t* d2h_bytes) {
+  return wfe_extract_host_ex(h, clips, lengths, batch, pcm_dtype, pcm_scale, do_normalize, out, WFE_OUT_F32, attn_mask,
+                             h2d_bytes, d2h_bytes);
 }
 
 }  // extern "C"

@@ -25,6 +25,7 @@
 // 400 = 16 x 25 Cooley-Tukey: n = n1 + 16*n2, k = k2 + 25*k1,
 //   X[k2+25k1] = sum_n1 W16^(n1 k1) * W400^(n1 k2) * sum_n2 x[n1+16 n2] W25^(n2 k2).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -89,6 +90,8 @@ template <>
 __device__ __forceinline__ float pcm_to_float<float>(float v, float) { return v; }
 template <>
 __device__ __forceinline__ float pcm_to_float<int16_t>(int16_t v, float scale) { return (float)v * scale; }
+template <>
+__device__ __forceinline__ float pcm_to_float<__half>(__half v, float) { return __half2float(v); }  // exact widening
 
 // one mel-stage work item: FOUR mel pairs (slot s: mels m_s, m_s+1, one per half-warp) that run in lock step over `trips`
 // table rows, so every thread has four independent accumulator chains.  Every (slot, half) filter is a contiguous BAND of

@@ -256,7 +256,13 @@ class WhisperFeatureExtractor:
         _lib.check(h.lib.wfe_logmel(h.ptr, pcm.data_ptr(), dt, pcm_scale, offsets.data_ptr(), len_ptr, batch, stats_ptr,
                                     out.data_ptr(), mask.data_ptr() if mask is not None else None,
                                     scratch.data_ptr(), stream), "wfe_logmel")
+        self._last_scratch = (h, scratch, batch)
         return out, mask
+
+    def debug_kernel_error(self) -> int:
+        """After a synchronize: non-zero if the last `logmel_device` launch gave up on an internal barrier (a bug)."""
+        h, scratch, batch = self._last_scratch
+        return int(h.lib.wfe_debug_scratch_error(h.ptr, scratch.data_ptr(), batch))
 
     def _extract_host(self, clips: Sequence[np.ndarray], n_samples: int, do_normalize: bool, want_mask: bool):
         """Host numpy clips -> host (pinned) torch tensors through the pipelined C entry point."""

@@ -30,7 +30,8 @@
  *   - "device" pointers must be valid on the handle's CUDA device.  The library never allocates or
  *     frees caller-visible buffers; the handle owns only its constant tables (and, for
  *     wfe_extract_host, its private pinned/device staging rings).
- *   - entry points are re-entrant: all per-call state lives in caller-provided scratch.
+ *   - entry points are re-entrant: all per-call state lives in caller-provided scratch (wfe_extract_host* serialise
+ *     on the handle's private staging ring).
  *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
  *     WFE_ERR_CUDA.
  */
@@ -44,7 +45,7 @@
 extern "C" {
 #endif
 
-#define WFE_ABI_VERSION 2
+#define WFE_ABI_VERSION 3
 
 typedef struct wfe_handle wfe_handle;
 
@@ -58,15 +59,25 @@ typedef enum wfe_status {
 
 typedef enum wfe_pcm_dtype {
   WFE_PCM_F32 = 0, /* float32 samples (what the reference decodes HDF5 audio to) */
-  WFE_PCM_I16 = 1  /* int16 samples, converted on load as (float)x * pcm_scale */
+  WFE_PCM_I16 = 1, /* int16 samples, converted on load as (float)x * pcm_scale */
+  WFE_PCM_F16 = 2  /* IEEE float16 samples, widened exactly on load (pcm_scale ignored) */
 } wfe_pcm_dtype;
+
+/* Element type of `input_features`.  F32 is what the reference extractor returns; F16 / BF16 fuse the cast the
+ * autocast consumer applies anyway (`fp16 = True`, ref:finetune/training/configs/largev3_debug.config:8): the value is
+ * the fp32 result rounded to nearest-even once, in the kernel's epilogue. */
+typedef enum wfe_out_dtype {
+  WFE_OUT_F32 = 0,
+  WFE_OUT_F16 = 1,
+  WFE_OUT_BF16 = 2
+} wfe_out_dtype;
 
 /* Mirrors the constructor arguments of WhisperFeatureExtractor (HF:...feature_extraction_whisper.py:69-80). */
 typedef struct wfe_config {
   int32_t n_mel;         /* feature_size: 80 (whisper-small) or 128 (large-v3); any 1..256 */
   int32_t n_fft;         /* must be 400 */
   int32_t hop_length;    /* must be 160 */
-  int32_t n_samples;     /* chunk_length * sampling_rate = 480000; any positive multiple of 160 */
+  int32_t n_samples;     /* chunk_length * sampling_rate = 480000; any value >= 400 (n_frames = n_samples / 160, rounded down) */
   int32_t sampling_rate; /* 16000 (informational; checked by the Python shim like HF does) */
   int32_t device;        /* CUDA device ordinal (LOCAL_RANK) */
 } wfe_config;
@@ -87,7 +98,7 @@ uint64_t wfe_launch_count(void);
 
 /* ---- log-mel features, device-resident input ---------------------------------------------------- */
 
-/* Bytes of device scratch wfe_logmel needs for `batch` clips (one max word per 32-frame tile, tile scheduler counter). */
+/* Bytes of device scratch wfe_logmel needs for `batch` clips (one max word per tile, tile scheduler counter, error word). */
 size_t wfe_logmel_scratch_bytes(const wfe_handle* h, int32_t batch);
 int32_t wfe_n_frames(const wfe_handle* h); /* n_samples / hop_length (3000) */
 
@@ -101,13 +112,27 @@ int32_t wfe_n_frames(const wfe_handle* h); /* n_samples / hop_length (3000) */
  *            (HF:feature_extraction_sequence_utils.py:265-278,327-332)
  * lengths    device, int64[batch] or NULL
  * norm_stats device, float2[batch] = (mean, 1/sqrt(var+1e-7)) from wfe_clip_stats, or NULL (do_normalize=False)
- * out        device, float32 (batch, n_mel, n_frames) C-contiguous  == BatchFeature["input_features"]
+ * out        device, float32 (batch, n_mel, n_frames) C-contiguous  == BatchFeature["input_features"]; 8-byte aligned
  * attn_mask  device, int32 (batch, n_frames) or NULL                == BatchFeature["attention_mask"]
  * scratch    device, wfe_logmel_scratch_bytes(h, batch) bytes; contents need not be initialised
  */
 int wfe_logmel(wfe_handle* h, const void* pcm, int32_t pcm_dtype, float pcm_scale, const int64_t* offsets,
                const int64_t* lengths, int32_t batch, const float* norm_stats, float* out, int32_t* attn_mask,
                void* scratch, void* stream);
+
+/* Same as wfe_logmel with `out` of element type out_dtype (wfe_out_dtype); `out` must be 16-byte aligned. */
+int wfe_logmel_ex(wfe_handle* h, const void* pcm, int32_t pcm_dtype, float pcm_scale, const int64_t* offsets,
+                  const int64_t* lengths, int32_t batch, const float* norm_stats, void* out, int32_t out_dtype,
+                  int32_t* attn_mask, void* scratch, void* stream);
+
+/* Which kernel the handle's standard configuration runs on: 1 = tcgen05 tensor-core kernel (n_samples = 480000,
+ * n_mel in {80, 128} with the slaney filter bank), 0 = CUDA-core kernel (any other geometry or filter bank).  The
+ * environment variable WFE_DISABLE_TC=1 forces 0 (A/B timing). */
+int32_t wfe_uses_tensor_cores(const wfe_handle* h);
+
+/* After the stream has been synchronised: non-zero if a kernel of a previous wfe_logmel call on `scratch` gave up
+ * waiting on an internal barrier (a bug, never expected).  `scratch`/`batch` as passed to that call. */
+int32_t wfe_debug_scratch_error(wfe_handle* h, const void* scratch, int32_t batch);
 
 /* Per-clip (mean, rstd) over the first min(len, n_samples) samples; stats: device float2[batch]. */
 int wfe_clip_stats(wfe_handle* h, const void* pcm, int32_t pcm_dtype, float pcm_scale, const int64_t* offsets,
@@ -144,6 +169,11 @@ int wfe_collate(wfe_handle* h, const int64_t* ids, const int64_t* offsets, int32
 int wfe_extract_host(wfe_handle* h, const void* const* clips, const int64_t* lengths, int32_t batch,
                      int32_t pcm_dtype, float pcm_scale, int32_t do_normalize, float* out, int32_t* attn_mask,
                      uint64_t* h2d_bytes, uint64_t* d2h_bytes);
+
+/* Same with `out` of element type out_dtype (halves the device->host bytes for F16 / BF16). */
+int wfe_extract_host_ex(wfe_handle* h, const void* const* clips, const int64_t* lengths, int32_t batch,
+                        int32_t pcm_dtype, float pcm_scale, int32_t do_normalize, void* out, int32_t out_dtype,
+                        int32_t* attn_mask, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
 
 #ifdef __cplusplus
 }

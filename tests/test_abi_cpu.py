@@ -38,7 +38,7 @@ def test_header_symbols_all_exported(pkg):
     for s in syms:
         assert hasattr(lib, s), f"libwfe.so does not export {s} declared in include/wfe.h"
     assert sorted(pkg._lib.SYMBOLS) == syms, "asr_finetune_b200._lib.SYMBOLS is out of sync with include/wfe.h"
-    assert lib.wfe_abi_version() == 2
+    assert lib.wfe_abi_version() == 3
     assert lib.wfe_launch_count() == 0 or lib.wfe_launch_count() > 0  # callable without a device
 
 
