@@ -91,7 +91,7 @@ struct wfe_handle {
   bool tc_ok = false;                  // the tcgen05 kernel applies (n_samples = 480000, baked slaney filter bank)
   uint4* d_tc_b = nullptr;             // DFT-100 operand, fp16 hi / lo, canonical UMMA layout
   float4* d_tc_tw = nullptr;           // W400^(n1 k2) twiddles of the epilogue
-  float* d_tc_win = nullptr;           // [400] periodic Hann
+  void* tc_encode = nullptr;           // cuTensorMapEncodeTiled, fetched through the runtime (no libcuda link)
   float4* d_s1_consts = nullptr;       // [8][25]
   float4* d_mel_tab = nullptr;           // [n_rows][2 halves]
   wfe::MelGroup* d_mel_groups = nullptr; // [n_groups]
@@ -185,16 +185,35 @@ int launch_tc(wfe_handle* h, const void* pcm, int pcm_dtype, float scale, const 
   p.tile_key = reinterpret_cast<uint32_t*>(scratch);
   p.b_mat = h->d_tc_b;
   p.tw = h->d_tc_tw;
-  p.win = h->d_tc_win;
   p.pcm_scale = scale;
   p.pcm_dtype = pcm_dtype;
   p.n_mel = kNMel;
   p.total_tiles = (uint32_t)total;
   uint32_t* err_flag = p.tile_key + (size_t)batch * h->ntiles + 1;
+  // 2-D view of the PCM for the raw-tile TMA: element (c, r) = pcm[c + 160 r]; a tile is the box (164 x 130) at
+  // (first sample, 0): rows of 160 samples land on a 164-float pitch.  Only float32, 16-byte aligned PCM uses it; any
+  // other input goes through the generic staging path and never touches the map (then it views a table of ours).
+  const bool tma_ok = pcm_dtype == WFE_PCM_F32 && (reinterpret_cast<uintptr_t>(pcm) & 15u) == 0;
+  CUtensorMap tmap;
+  {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    const cuuint64_t gdim[2] = {(cuuint64_t)1 << 31, (cuuint64_t)wfe::tc::kRawRows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)wfe::kHop * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)wfe::tc::kRawPitch, (cuuint32_t)wfe::tc::kRawRows};
+    const cuuint32_t estr[2] = {1, 1};
+    void* base = tma_ok ? const_cast<void*>(pcm) : static_cast<void*>(h->d_tc_b);
+    const CUresult cr = reinterpret_cast<EncodeFn>(h->tc_encode)(
+        &tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(WFE_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)cr) + ")");
+  }
+  if (!tma_ok && pcm_dtype == WFE_PCM_F32) p.pcm_dtype = 3;  // float32 at an odd address: generic staging only
   WFE_CUDA(cudaMemsetAsync(scratch, 0, scratch_bytes(h, batch), st));
   long long grid = h->sm_count;
   if (grid > total) grid = total;
-  wfe::tc::logmel_tc_kernel<OutT, kNMel><<<(unsigned)grid, wfe::tc::kThreads, wfe::tc::kSmemBytes, st>>>(p, err_flag);
+  wfe::tc::logmel_tc_kernel<OutT, kNMel><<<(unsigned)grid, wfe::tc::kThreads, wfe::tc::kSmemBytes, st>>>(p, tmap, err_flag);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   WFE_CUDA(cudaGetLastError());
   return WFE_OK;
@@ -387,15 +406,20 @@ int setup_tensor_core_path(wfe_handle* h, const float* mel_filters) {
         t[2 + e2] = (float)sin(ang);
       }
     }
-  float win[wfe::kNFft];
-  float2 unused_tw[16 * 12];
-  wfe::fill_tables(win, unused_tw);
-  if (cudaMalloc((void**)&h->d_tc_b, kBBytes) != cudaSuccess || cudaMalloc((void**)&h->d_tc_tw, kTwBytes) != cudaSuccess ||
-      cudaMalloc((void**)&h->d_tc_win, sizeof(win)) != cudaSuccess)
+  {
+    cudaDriverEntryPointQueryResult qres;
+    void* fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || fn == nullptr ||
+        qres != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      return WFE_OK;  // driver without tensor maps: stay on the CUDA-core kernel
+    }
+    h->tc_encode = fn;
+  }
+  if (cudaMalloc((void**)&h->d_tc_b, kBBytes) != cudaSuccess || cudaMalloc((void**)&h->d_tc_tw, kTwBytes) != cudaSuccess)
     return fail(WFE_ERR_NOMEM, "cudaMalloc failed for the tensor-core tables");
   WFE_CUDA(cudaMemcpy(h->d_tc_b, bmat.data(), kBBytes, cudaMemcpyHostToDevice));
   WFE_CUDA(cudaMemcpy(h->d_tc_tw, tw.data(), kTwBytes, cudaMemcpyHostToDevice));
-  WFE_CUDA(cudaMemcpy(h->d_tc_win, win, sizeof(win), cudaMemcpyHostToDevice));
 #ifdef WFE_EXP_MINIMAL
   WFE_CUDA(cudaFuncSetAttribute(wfe::tc::logmel_tc_kernel<float, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)wfe::tc::kSmemBytes));
@@ -594,7 +618,6 @@ void wfe_destroy(wfe_handle* h) {
   if (h->d_mel_groups) cudaFree(h->d_mel_groups);
   if (h->d_tc_b) cudaFree(h->d_tc_b);
   if (h->d_tc_tw) cudaFree(h->d_tc_tw);
-  if (h->d_tc_win) cudaFree(h->d_tc_win);
   delete h;
 }
 

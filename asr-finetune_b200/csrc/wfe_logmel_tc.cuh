@@ -11,24 +11,41 @@
 //   DFT-100 matrix, the same for every n1.  fp32 accuracy on fp16 tensor cores by operand splitting: a = a_hi + a_lo,
 //   b = b_hi + b_lo (fp16 each), D = a_hi b_hi + a_hi b_lo + a_lo b_hi with fp32 accumulation in TMEM; the frame tile is
 //   pre-scaled by a power of two so that its largest sample sits in [2^14, 2^15) (undone exactly in the log domain).
-//   Measured (tools/ubench_tcgen05.cu, profiles/r02_ubench_tcgen05.txt): 2^-19.6 of the row maximum, 60.8 cycles per
-//   128x112x16 MMA.
+//   Measured (tools/ubench_tcgen05.cu, profiles/r02_ubench_tcgen05.txt): 2^-19.6 of the row maximum.
+//
+// Data movement.  A first version kept the A operand in a shared-memory ring: the role trace (tools/tc_trace.py) showed
+// the kernel bound by SHARED-MEMORY BANDWIDTH -- an SS-mode 128x112x16 MMA fetches 7.5 KB of operands (60.8 cycles at
+// 128 B/clk, the whole pipe) and the prep warps' own LDS/STS came on top: 1400 cycles per k-step.  So:
+//   * A lives in TENSOR MEMORY: the prep threads (thread = frame = TMEM lane) write their fp16 hi/lo rows with tcgen05.st
+//     into the 64 columns the accumulators leave free (4 slots, one per n1, one k-step each); the MMA reads A from TMEM
+//     (57 cycles per MMA) and only B (3.5 KB) from shared memory;
+//   * the raw tile arrives by ONE 2-D TMA (cp.async.bulk.tensor, box 164 x 130 floats over a 640-byte-pitch view of the
+//     clip: the 4 extra floats per row pad each hop row to 164 words, so LDS.128 by frame is bank-conflict-free); the
+//     first version issued 130 row copies and spent 9.4 k cycles just issuing them;
+//   * raw tiles are double-buffered, so the load of tile t+1 overlaps everything of tile t.
+//
+//   * TMEM is full (4 x 112 accumulator columns + 64 operand columns of 512), so the accumulators cannot be double-
+//     buffered: a tile's MMA phase and its epilogue phase alternate.  Both phases are latency-bound per warp, so the
+//     eight WORKER warps (two per SM sub-partition and TMEM lane quarter) take part in BOTH: in the MMA phase the two
+//     warps of a quarter prepare alternate k-steps; in the epilogue each takes half of the k2 range, and the few mel
+//     filters fed by both halves are completed through a 2.5 KB shared-memory exchange.
 //
 // One persistent CTA per SM, 11 warps, tile = 128 consecutive frames of one clip (24 tiles per 30-s clip), tile ids
 // strided statically over the CTAs (every role derives the same sequence):
-//   warps 0-3   PREP      thread = frame: raw samples (smem) -> window, scale, split hi/lo -> A operand ring (smem,
-//                         K-major no-swizzle core matrices, one stage = one k-step of 16 n2 for all four n1)
-//   warps 4-7   EPILOGUE  thread = frame = TMEM lane: tcgen05.ld, twiddle + DFT-4 + power (packed f32x2), banded mel with
-//                         immediate weights (generated straight-line code), log10, (x+4)/4, store, tile min/max
-//   warp  8     MMA       lane 0 issues 12 tcgen05.mma per k-step (4 n1 x 3 passes), commits to mbarriers
-//   warp  9     LOADER    raw tile: 130 cp.async.bulk row copies (TMA) into a padded hop-row layout
+//   warps 0-7   WORKERS   thread = frame = TMEM lane (quarter = warp % 4, half = warp / 4)
+//               prep:     raw samples (smem) -> scale, window (FMUL immediates), split hi/lo -> TMEM (tcgen05.st)
+//               epilogue: tcgen05.ld, twiddle + DFT-4 + power (packed f32x2), banded mel with immediate weights
+//                         (generated straight-line code), log10, (x+4)/4, store, tile min/max
+//   warp  8     MMA       one elected lane issues 3 tcgen05.mma per (k-step, n1) slot, commits to mbarriers
+//   warp  9     LOADER    one TMA per tile
 //   warp 10     CLAMP     per-clip max-8 clamp books (same scheme as wfe_logmel.cuh: one published key per tile, fix-ups
 //                         of this CTA's own tiles from L2 once their clip is complete)
-// Specialised for n_samples = 480000 (3000 frames), fp32 accumulate, n_mel in {80, 128} with the slaney structure baked by
+// Specialised for n_samples = 480000 (3000 frames), n_mel in {80, 128} with the slaney structure baked by
 // tools/gen_tc_epilogue.py; everything else runs on the CUDA-core kernel.
 #pragma once
-#include <cuda_fp16.h>
+#include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -49,26 +66,38 @@ constexpr int kRawPitch = kHop + 4;               // floats: lane stride 164 = 4
 constexpr int kRawFloats = kRawRows * kRawPitch;  // 21320
 constexpr int kKSteps = 7;                        // 100 n2 padded to 112 = 7 x 16
 constexpr int kN = 112;                           // MMA N: 52 k2 x (re, im) = 104, padded to a multiple of 16
-constexpr int kChunkBytes = kTileM * 16;          // one 8-element K chunk of 128 rows
-constexpr int kStageBytes = 4 * 2 * 2 * kChunkBytes;  // [n1][hi/lo][chunk][row][16 B] = 32768
-constexpr int kStages = 2;
 constexpr int kBChunkBytes = kN * 16;             // 1792
 constexpr int kBBytes = 2 * 14 * kBChunkBytes;    // [hi/lo][chunk 14][n 112][16 B] = 50176
 constexpr int kTwBytes = 26 * 3 * 16;             // [pair][n1-1] (cos_k2, cos_k2+1, sin_k2, sin_k2+1)
 constexpr int kThreads = 11 * 32;
 constexpr int kTmemCols = 512;
+constexpr int kTmemA = 4 * kN;                    // columns 448..511: A slots, 16 columns per n1 (8 hi + 8 lo)
 constexpr int kRing = 128;
+constexpr int kRawBoxBytes = kRawRows * kRawPitch * 4;              // 85280: what one TMA delivers
+constexpr int kRawBufBytes = (kRawBoxBytes + 127) & ~127;           // 85376: TMA destinations are 128-byte aligned
 
 constexpr size_t kSmemRaw = 0;
-constexpr size_t kSmemA = kSmemRaw + (size_t)kRawFloats * 4;          // 85280
-constexpr size_t kSmemB = kSmemA + (size_t)kStages * kStageBytes;     // +65536
-constexpr size_t kSmemWs = kSmemB + kBBytes;                          // +50176
-constexpr size_t kSmemTw = kSmemWs + 400 * 4;
-constexpr size_t kSmemBytes = kSmemTw + kTwBytes;                     // 203840
+constexpr size_t kSmemB = kSmemRaw + 2 * (size_t)kRawBufBytes;       // 170752
+constexpr size_t kSmemTw = kSmemB + kBBytes;                         // +50176
+constexpr size_t kSmemWs = kSmemTw + kTwBytes;                       // scaled window, 7 x 64 entries (zero beyond 400)
+constexpr size_t kSmemBytes = kSmemWs + kKSteps * 64 * 4;            // 223968
+
+#define WFE_TC_GEN_WINDOW 1
+#include "wfe_tc_epilogue_gen.inc"
+#undef WFE_TC_GEN_WINDOW
+#define WFE_TC_GEN_COUNTS 1
+#define WFE_TC_GEN_NMEL 80
+#include "wfe_tc_epilogue_gen.inc"
+#undef WFE_TC_GEN_NMEL
+#define WFE_TC_GEN_NMEL 128
+#include "wfe_tc_epilogue_gen.inc"
+#undef WFE_TC_GEN_NMEL
+#undef WFE_TC_GEN_COUNTS
+constexpr int kMaxShared = kTcShared80 > kTcShared128 ? kTcShared80 : kTcShared128;  // filters fed by both epilogue halves
 
 #ifdef WFE_TC_TRACE
 // timing-trace build (diagnostics only): CTA 0 stamps clock64() at role milestones of its tile iterations 4..11
-constexpr int kTrTiles = 8, kTrRoles = 5, kTrPts = 16;
+constexpr int kTrTiles = 8, kTrRoles = 5, kTrPts = 32;
 __device__ unsigned long long g_tc_trace[kTrTiles * kTrRoles * kTrPts];
 #define TCT(role, it, pt)                                                                      \
   do {                                                                                         \
@@ -91,16 +120,15 @@ struct TcParams {
   uint32_t* tile_key;       // [B][24]
   const uint4* b_mat;       // kBBytes: DFT-100 operand, canonical layout, hi then lo
   const float4* tw;         // kTwBytes: twiddles W400^(n1 k2)
-  const float* win;         // [400] periodic Hann, fp32
   float pcm_scale;
-  int pcm_dtype;            // 0 = float32, 1 = int16, 2 = float16 (wfe_pcm_dtype)
+  int pcm_dtype;            // 0 = float32, 1 = int16, 2 = float16 (wfe_pcm_dtype); 3 = float32 the TMA cannot address
   int n_mel;
   uint32_t total_tiles;
 };
 
 // the generic staging path (tile edges, 2-byte PCM, normalisation) is the only place the PCM element type matters
 __device__ __forceinline__ float load_pcm(const void* pcm, int dtype, int64_t i, float scale) {
-  if (dtype == 0) return reinterpret_cast<const float*>(pcm)[i];
+  if (dtype == 0 || dtype == 3) return reinterpret_cast<const float*>(pcm)[i];
   if (dtype == 1) return (float)reinterpret_cast<const int16_t*>(pcm)[i] * scale;
   return __half2float(reinterpret_cast<const __half*>(pcm)[i]);
 }
@@ -132,41 +160,77 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
 #ifndef WFE_TC_WAIT
 #define WFE_TC_WAIT 1  // 0: bare try_wait spin, 1: try_wait with a suspend-time hint, 2: nanosleep back-off between polls
 #endif
-__device__ __forceinline__ bool mbar_try_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
-      : "memory");
-  return ok != 0;
-}
-// Waits for the phase with the given parity.  Gives up after a few seconds so that a protocol bug turns into a wrong
-// answer + error flag instead of a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t* err_flag) {
-  if (mbar_try(bar, parity)) return;
+// Waits for the phase with the given parity.  The fast path is one try_wait; the slow path is out of line (the kernel's
+// straight-line code is instruction-cache bound: ~40 inlined copies of the loop cost 25 KB) and gives up after a few
+// seconds, so that a protocol bug turns into a wrong answer + error flag instead of a hung GPU.
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t parity, uint32_t* err_flag) {
   const long long t0 = clock64();
 #pragma unroll 1
   for (uint32_t spin = 0;; ++spin) {
+    uint32_t ok;
 #if WFE_TC_WAIT == 2
     __nanosleep(40);
-    if (mbar_try(bar, parity)) return;
-#elif WFE_TC_WAIT == 1
-    if (mbar_try_hint(bar, parity, 4000u)) return;
-#else
-    if (mbar_try(bar, parity)) return;
 #endif
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+#if WFE_TC_WAIT == 1
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 4000;\n\t"
+#else
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#endif
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar_addr), "r"(parity)
+        : "memory");
+    if (ok) return;
     if ((spin & 1023u) == 1023u && clock64() - t0 > 6000000000ll) break;
   }
   if (err_flag != nullptr) atomicExch(err_flag, 0xDEADu);
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t* err_flag) {
+  if (mbar_try(bar, parity)) return;
+  mbar_wait_slow(smem_u32(bar), parity, err_flag);
 }
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_u32(smem_dst)),
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+// one 2-D tiled TMA: box (164 floats x 130 rows) at element coordinates (c0, c1) of the tensor map -> shared memory
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int32_t c0, int32_t c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] . B[smem]: A is 128 lanes x 8 columns (16 fp16, two per 32-bit column)
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// true in exactly one (elected) lane of the converged warp: tcgen05.mma / commit / TMA are issued from inside
+// `if (elect_one())` so that the compiler sees a single active thread and emits no per-lane serialisation loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols)
@@ -217,8 +281,9 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
 // ---------------------------------------------------------------------------------------------------------------
 // tile geometry: every role derives it from the tile id alone
 // ---------------------------------------------------------------------------------------------------------------
+constexpr int kModeAsyncHead = 3;
 struct Tile {
-  int b, tile, len, mode;  // mode: kModeSilent / kModeAsync (TMA bulk) / kModeSync (generic staging)
+  int b, tile, len, mode;  // mode: kModeSilent / kModeAsync (TMA) / kModeAsyncHead (TMA + reflect patch) / kModeSync (generic)
   int64_t off;
 };
 __device__ __forceinline__ Tile tile_info(const TcParams& p, uint32_t id) {
@@ -237,10 +302,18 @@ __device__ __forceinline__ Tile tile_info(const TcParams& p, uint32_t id) {
   if (lowest >= t.len) {
     t.mode = kModeSilent;
   } else {
+    // TMA: the whole 164 x 130 box (row pitch 160 floats) must lie inside the clip, start on a 16-byte boundary and
+    // be addressable with an int32 element coordinate
     const float* src = reinterpret_cast<const float*>(p.pcm) + t.off + s_begin;
-    const bool bulk = p.pcm_dtype == 0 && p.norm == nullptr && s_begin >= 0 && s_begin + kRawLen <= t.len &&
-                      (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
-    t.mode = bulk ? kModeAsync : kModeSync;
+    // (the first tile of a clip starts 200 samples early: those land as whatever precedes the clip -- zeros if nothing
+    //  does, the TMA fills out-of-range coordinates with zeros -- and are overwritten by the reflect pad afterwards)
+    //  -- provided the clip does not start the buffer: the TMA bounds-checks the COORDINATE, not the address, and would
+    //  zero-fill the head of every row whose column coordinate is negative)
+    const bool bulk = p.pcm_dtype == 0 && p.norm == nullptr && (s_begin >= 0 || t.tile == 0) &&
+                      s_begin + (kRawRows - 1) * kHop + kRawPitch <= t.len &&
+                      (reinterpret_cast<uintptr_t>(src) & 15u) == 0 && t.off + s_begin < (int64_t)0x7fff0000 &&
+                      t.off + s_begin >= 0;
+    t.mode = bulk ? (s_begin >= 0 ? kModeAsync : kModeAsyncHead) : kModeSync;
   }
   return t;
 }
@@ -318,49 +391,58 @@ __device__ __forceinline__ float wait_clip_floor_tc(const uint32_t* tile_key, in
   }
 }
 
-// named barrier among the 128 prep threads
-__device__ __forceinline__ void prep_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// named barrier among the 256 worker threads
+__device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------
 template <typename OutT, int kNMel>
-__global__ void __launch_bounds__(kThreads, 1) logmel_tc_kernel(const TcParams p, uint32_t* err_flag) {
+__global__ void __launch_bounds__(kThreads, 1)
+    logmel_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap, uint32_t* err_flag) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  float* const raw = reinterpret_cast<float*>(smem + kSmemRaw);
-  uint8_t* const a_ring = smem + kSmemA;
   uint8_t* const b_sm = smem + kSmemB;
-  float* const ws = reinterpret_cast<float*>(smem + kSmemWs);
   const float4* const tw_sm = reinterpret_cast<const float4*>(smem + kSmemTw);
+  float* const ws = reinterpret_cast<float*>(smem + kSmemWs);
 
-  __shared__ uint64_t bar_raw_full, bar_raw_empty, bar_a_full[kStages], bar_a_empty[kStages], bar_d_full, bar_d_empty,
+  __shared__ uint64_t bar_raw_full[2], bar_raw_empty[2], bar_a_full[4], bar_a_empty[2][4], bar_d_full, bar_d_empty,
       bar_st_full[2], bar_st_empty[2];
   __shared__ uint32_t s_tmem;
-  __shared__ uint32_t s_pmax[4];        // prep: per-warp max |x| bits
-  __shared__ float s_tilek[2];          // per tile parity: additive constant of the log-domain un-scaling
-  __shared__ float s_red[2][2][4];      // [tile parity][max, min][epilogue warp] of y over the warp's 32 frames
+  __shared__ uint32_t s_pmax[8];        // prep: per-warp max |x| bits
+  __shared__ float s_red[2][2][8];      // [tile parity][max, min][worker warp] of y over the warp's share of the tile
+  __shared__ float s_part[kMaxShared * kTileM];  // epilogue half 1 -> half 0: partial sums of the shared mel filters
   __shared__ int2 s_pend_bt[kRing];
   __shared__ float2 s_pend_mm[kRing];
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform: role branches do not diverge
+#ifdef WFE_TC_TRACE
+  if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 77)) {  // whole-kernel span of two CTAs: SM clock and wall clock
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    g_tc_trace[(4 + (blockIdx.x ? 5 : 0)) * kTrPts + 0] = clock64();
+    g_tc_trace[(4 + (blockIdx.x ? 5 : 0)) * kTrPts + 1] = gt;
+  }
+#endif
 
   // ---- one-time set-up ----
   for (int i = tid; i < kBBytes / 16; i += kThreads) reinterpret_cast<uint4*>(b_sm)[i] = p.b_mat[i];
   for (int i = tid; i < kTwBytes / 16; i += kThreads) reinterpret_cast<float4*>(smem + kSmemTw)[i] = p.tw[i];
   fence_async_smem();  // B is read by the tensor core (async proxy)
   if (tid == 0) {
-    mbar_init(&bar_raw_full, 1);
-    mbar_init(&bar_raw_empty, 128);
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&bar_a_full[s], 128);
-      mbar_init(&bar_a_empty[s], 1);
-    }
-    mbar_init(&bar_d_full, 1);
-    mbar_init(&bar_d_empty, 128);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&bar_st_full[s], 4);
+      mbar_init(&bar_raw_full[s], 1);
+      mbar_init(&bar_raw_empty[s], 256);
+      mbar_init(&bar_st_full[s], 8);
       mbar_init(&bar_st_empty[s], 1);
     }
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(&bar_a_full[s], 128);
+      mbar_init(&bar_a_empty[0][s], 1);
+      mbar_init(&bar_a_empty[1][s], 1);
+    }
+    mbar_init(&bar_d_full, 1);
+    mbar_init(&bar_d_empty, 256);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 9) tmem_alloc(&s_tmem, kTmemCols);
@@ -369,45 +451,104 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_tc_kernel(const TcParams p
   tc_fence_after();
   const uint32_t tmem = s_tmem;
 
-  if (warp < 4) {
-    // =========================================== PREP ===========================================
-    const int m = tid;  // frame within the tile
-    const float* const xrow = raw + m * kRawPitch;
-    uint32_t ks = 0;   // running k-step count (A ring position)
+  if (warp < 8) {
+    // =========================================== WORKERS ===========================================
+    const int qt = warp & 3;                 // TMEM lane quarter: lanes 32 qt .. 32 qt + 31
+    const int hh = warp >> 2;                // which of the quarter's two warps
+    const int m = qt * 32 + lane;            // frame within the tile == TMEM lane
+    const int wt = tid;                      // 0..255 among the workers
+    const uint32_t tlane = tmem + ((uint32_t)(qt * 32) << 16);
+    const uint32_t a_slot0 = tlane + kTmemA;
+    uint32_t ks = 0;   // running k-step count
     uint32_t nt = 0;   // running count of non-silent tiles
     for (uint32_t id = blockIdx.x; id < p.total_tiles; id += gridDim.x) {
       const Tile t = tile_info(p, id);
       if (t.mode == kModeSilent) continue;
-      if (tid == 0) TCT(0, nt, 0);
-      mbar_wait(&bar_raw_full, nt & 1, err_flag);
-      if (tid == 0) TCT(0, nt, 1);
-      if (t.mode == kModeSync) {
-        // generic staging: truncate / right-zero-pad to 30 s, centred reflect pad, dtype conversion, normalisation
-        const int s_begin = t.tile * kTileM * kHop - kNFft / 2;
+      const uint32_t rb = nt & 1u;
+      float* const raw = reinterpret_cast<float*>(smem + kSmemRaw + rb * kRawBufBytes);
+      const float* const xrow = raw + m * kRawPitch;
+      const int t0 = t.tile * kTileM;
+      const int s_begin = t0 * kHop - kNFft / 2;
+      if (wt == 0) TCT(0, nt, 0);
+      mbar_wait(&bar_raw_full[rb], (nt >> 1) & 1u, err_flag);
+      if (wt == 0) TCT(0, nt, 1);
+      if (t.mode == kModeAsyncHead) {
+        // first tile of a clip: the TMA started 200 samples before the clip; replace them by the centred reflect pad
+        if (wt < kNFft / 2) {
+          const int s = kNFft / 2 - wt;  // raw[i] = x[200 - i]
+          raw[wt + (wt >= kHop ? kRawPitch - kHop : 0)] = s < t.len ? load_pcm(p.pcm, p.pcm_dtype, t.off + s, p.pcm_scale) : 0.f;
+        }
+        worker_bar();
+      } else if (t.mode == kModeSync) {
+        // generic staging: truncate / right-zero-pad to 30 s, centred reflect pad, dtype conversion, normalisation.
+        // Only the rows the tile's valid frames read; quads of samples, eight quads in flight per thread.
+        const int nvalid = min(kTileM, kNFrames - t0);
+        const int n_quads = ((nvalid - 1) * kHop + kNFft + 3) / 4;
         float mean = 0.f, rstd = 1.f;
         if (p.norm != nullptr) {
           const float2 st = __ldg(p.norm + t.b);
           mean = st.x;
           rstd = st.y;
         }
-        for (int i = tid; i < kRawRows * kHop; i += 128) {
-          int s = s_begin + i;
-          if (s < 0) s = -s;
-          if (s >= kNSamples) s = 2 * (kNSamples - 1) - s;
-          float v = 0.f;
-          if (s >= 0 && s < t.len) {
-            v = load_pcm(p.pcm, p.pcm_dtype, t.off + s, p.pcm_scale);
-            if (p.norm != nullptr) v = (v - mean) * rstd;
+        const bool vec_ok = (p.pcm_dtype == 0 || p.pcm_dtype == 3) &&
+                            ((reinterpret_cast<uintptr_t>(reinterpret_cast<const float*>(p.pcm) + t.off + s_begin) & 15u) == 0);
+        constexpr int kBatch = 8;
+        for (int g0 = wt; g0 < n_quads; g0 += 256 * kBatch) {
+          float4 v[kBatch];
+#pragma unroll
+          for (int u = 0; u < kBatch; ++u) {
+            const int i = 4 * (g0 + 256 * u);
+            const int s = s_begin + i;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (g0 + 256 * u < n_quads) {
+              if (vec_ok && s >= 0 && s + 3 < t.len) {  // interior (t.len <= n_samples: no reflection either)
+                v[u] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.pcm) + t.off + s));
+              } else {
+                float e[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  int sk = s + k;
+                  if (sk < 0) sk = -sk;
+                  if (sk >= kNSamples) sk = 2 * (kNSamples - 1) - sk;
+                  e[k] = (sk >= 0 && sk < t.len) ? load_pcm(p.pcm, p.pcm_dtype, t.off + sk, p.pcm_scale) : 0.f;
+                }
+                v[u] = make_float4(e[0], e[1], e[2], e[3]);
+              }
+            }
           }
-          const int r = i / kHop;
-          raw[r * kRawPitch + (i - r * kHop)] = v;
+#pragma unroll
+          for (int u = 0; u < kBatch; ++u) {
+            const int g = g0 + 256 * u;
+            if (g < n_quads) {
+              float4 x = v[u];
+              if (p.norm != nullptr) {
+                const int s = s_begin + 4 * g;
+                float* e = reinterpret_cast<float*>(&x);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  int sk = s + k;
+                  if (sk < 0) sk = -sk;
+                  if (sk >= kNSamples) sk = 2 * (kNSamples - 1) - sk;
+                  if (sk >= 0 && sk < t.len) e[k] = (e[k] - mean) * rstd;
+                }
+              }
+              const int r = g / (kHop / 4);
+              *reinterpret_cast<float4*>(raw + r * kRawPitch + 4 * (g - r * (kHop / 4))) = x;
+            }
+          }
         }
-        prep_bar();
+        // rows beyond the valid frames are read by the idle lanes' arithmetic: make them finite
+        for (int g = n_quads + wt; g < kRawRows * (kHop / 4); g += 256) {
+          const int r = g / (kHop / 4);
+          *reinterpret_cast<float4*>(raw + r * kRawPitch + 4 * (g - r * (kHop / 4))) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        worker_bar();
       }
-      if (tid == 0) TCT(0, nt, 2);
-      // ---- tile maximum -> power-of-two scale, scaled window table ----
+      if (wt == 0) TCT(0, nt, 2);
+      // ---- tile maximum -> power-of-two scale ----
       uint32_t mx = 0;
-      for (int i = tid; i < kRawRows * (kHop / 4); i += 128) {
+#pragma unroll 4
+      for (int i = wt; i < kRawRows * (kHop / 4); i += 256) {
         const int r = i / (kHop / 4), c = i - r * (kHop / 4);
         float4 v = *reinterpret_cast<const float4*>(raw + r * kRawPitch + 4 * c);
         if (r == kRawRows - 1 && 4 * c >= kRawLen - (kRawRows - 1) * kHop) v = make_float4(0.f, 0.f, 0.f, 0.f);  // beyond the tile
@@ -416,132 +557,117 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_tc_kernel(const TcParams p
       }
       mx = __reduce_max_sync(0xffffffffu, mx);
       if (lane == 0) s_pmax[warp] = mx;
-      prep_bar();
-      mx = max(max(s_pmax[0], s_pmax[1]), max(s_pmax[2], s_pmax[3]));
+      worker_bar();
+      mx = max(max(max(s_pmax[0], s_pmax[1]), max(s_pmax[2], s_pmax[3])), max(max(s_pmax[4], s_pmax[5]), max(s_pmax[6], s_pmax[7])));
       // scale = 2^(14 - e) with e = unbiased exponent of the maximum (clamped so that the scale stays a normal float)
       int e = (int)((mx >> 23) & 0xffu) - 127;
       if (mx == 0u) e = 14;
       e = max(-100, min(e, 100));
       const float scale = __uint_as_float((uint32_t)(127 + 14 - e) << 23);
-      if (tid < 100) {
-        const float4 w = __ldg(reinterpret_cast<const float4*>(p.win) + tid);
-        reinterpret_cast<float4*>(ws)[tid] = make_float4(w.x * scale, w.y * scale, w.z * scale, w.w * scale);
-      }
-      if (tid == 0) {
-        // y = (log10(mel_scaled * 2^(-2 (14 - e))) + 4) / 4 = lg2(mel_scaled) * C + (1 - 2 (14 - e) C)
-        s_tilek[nt & 1] = 1.0f - (float)(2 * (14 - e)) * (0.25f * kLog10_2);
-      }
-      prep_bar();
-      if (tid == 0) TCT(0, nt, 3);
-
-      // ---- k-steps: 16 n2 (= 64 consecutive samples) for all four n1 ----
+      // y = (log10(mel_scaled * 2^(-2 (14 - e))) + 4) / 4 = lg2(mel_scaled) * C + (1 - 2 (14 - e) C)
+      const float tile_k = 1.0f - (float)(2 * (14 - e)) * (0.25f * kLog10_2);
+      // scaled window table (exact: the scale is a power of two), zero beyond the 400-point frame: with it the k-step
+      // loop below needs no per-k-step code (a fully unrolled version with FMUL immediates was instruction-cache bound)
+      if (wt < kKSteps * 16) {
+        float w4[4];
 #pragma unroll
-      for (int j = 0; j < kKSteps; ++j, ++ks) {  // unrolled: every smem offset below is an immediate
-        const uint32_t stage = ks & 1u;
-        mbar_wait(&bar_a_empty[stage], ((ks >> 1) & 1u) ^ 1u, err_flag);
-        uint8_t* const st_base = a_ring + stage * kStageBytes + m * 16;
-        const int nq = (j == kKSteps - 1) ? 4 : 16;  // valid n2 in this k-step (n2 < 100)
+        for (int k = 0; k < 4; ++k) w4[k] = (4 * wt + k < kNFft) ? __uint_as_float(kWinBits[4 * wt + k]) * scale : 0.f;
+        reinterpret_cast<float4*>(ws)[wt] = make_float4(w4[0], w4[1], w4[2], w4[3]);
+      }
+      worker_bar();  // ws complete; s_pmax may be rewritten by the next tile only after everybody has read it
+      if (wt == 0) TCT(0, nt, 3);
+
+      // ---- MMA phase: k-steps of 16 n2 (= 64 consecutive samples) for all four n1; the quarter's two warps take
+      //      alternate k-steps ----
+#pragma unroll 1
+      for (int j = (int)((ks & 1u) ^ (uint32_t)hh); j < kKSteps; j += 2) {
+        const uint32_t kj = ks + (uint32_t)j;  // running k-step index
+        uint32_t hv[4][8], lv[4][8];           // per n1: 16 fp16 hi (K order), 16 fp16 lo
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
+          // the 32 samples of a half k-step never straddle a hop row (160 = 5 x 32)
+          const int n0 = 64 * j + 32 * c;
+          const float* xp = xrow + n0 + (kRawPitch - kHop) * ((n0 >= kHop ? 1 : 0) + (n0 >= 2 * kHop ? 1 : 0));
+          const float* wp = ws + n0;
           float h[4][8], l[4][8];
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const int qq = 8 * c + q;
-            if (qq < nq) {
-              const int n = 64 * j + 4 * qq;  // sample index within the frame
-              const int roff = (n / kHop) * kRawPitch + (n % kHop);
-              const float4 x = *reinterpret_cast<const float4*>(xrow + roff);
-              const float4 w = *reinterpret_cast<const float4*>(ws + n);
-              const float y[4] = {x.x * w.x, x.y * w.y, x.z * w.z, x.w * w.w};
+            const float4 x = *reinterpret_cast<const float4*>(xp + 4 * q);
+            const float4 w = *reinterpret_cast<const float4*>(wp + 4 * q);
+            const float y[4] = {x.x * w.x, x.y * w.y, x.z * w.z, x.w * w.w};
 #pragma unroll
-              for (int n1 = 0; n1 < 4; ++n1) {
-                const float hh = __uint_as_float(__float_as_uint(y[n1]) & 0xFFFFE000u);  // 11 significant bits: exact in fp16
-                h[n1][q] = hh;
-                l[n1][q] = y[n1] - hh;
-              }
-            } else {
-#pragma unroll
-              for (int n1 = 0; n1 < 4; ++n1) {
-                h[n1][q] = 0.f;
-                l[n1][q] = 0.f;
-              }
+            for (int n1 = 0; n1 < 4; ++n1) {
+              const float hb = __uint_as_float(__float_as_uint(y[n1]) & 0xFFFFE000u);  // 11 significant bits: exact in fp16
+              h[n1][q] = hb;
+              l[n1][q] = y[n1] - hb;
             }
           }
 #pragma unroll
-          for (int n1 = 0; n1 < 4; ++n1) {
-            const uint4 hv = make_uint4(pack_h2(h[n1][0], h[n1][1]), pack_h2(h[n1][2], h[n1][3]),
-                                        pack_h2(h[n1][4], h[n1][5]), pack_h2(h[n1][6], h[n1][7]));
-            const uint4 lv = make_uint4(pack_h2(l[n1][0], l[n1][1]), pack_h2(l[n1][2], l[n1][3]),
-                                        pack_h2(l[n1][4], l[n1][5]), pack_h2(l[n1][6], l[n1][7]));
-            *reinterpret_cast<uint4*>(st_base + ((n1 * 2 + 0) * 2 + c) * kChunkBytes) = hv;
-            *reinterpret_cast<uint4*>(st_base + ((n1 * 2 + 1) * 2 + c) * kChunkBytes) = lv;
-          }
+          for (int n1 = 0; n1 < 4; ++n1)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              hv[n1][4 * c + u] = pack_h2(h[n1][2 * u], h[n1][2 * u + 1]);
+              lv[n1][4 * c + u] = pack_h2(l[n1][2 * u], l[n1][2 * u + 1]);
+            }
         }
-        fence_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
-        mbar_arrive(&bar_a_full[stage]);
-        if (tid == 0) TCT(0, nt, 4 + j);
+        // ---- hand the four slots to the tensor core as they become free ----
+#pragma unroll
+        for (int n1 = 0; n1 < 4; ++n1) {
+          // The MMAs of k-step kj - 1 have read this slot.  Their commits go to the barrier set of THAT k-step's parity:
+          // a parity wait cannot tell phase i from phase i + 2, and with the quarter's two warps alternating k-steps a
+          // single set would let a warp run two phases ahead.  This way each warp consumes every phase of "its" set.
+          mbar_wait(&bar_a_empty[hh ^ 1][n1], hh ? ((kj >> 1) & 1u) : (((kj >> 1) & 1u) ^ 1u), err_flag);
+          tc_fence_after();
+          const uint32_t r[16] = {hv[n1][0], hv[n1][1], hv[n1][2], hv[n1][3], hv[n1][4], hv[n1][5], hv[n1][6], hv[n1][7],
+                                  lv[n1][0], lv[n1][1], lv[n1][2], lv[n1][3], lv[n1][4], lv[n1][5], lv[n1][6], lv[n1][7]};
+          tmem_st16(a_slot0 + 16 * n1, r);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&bar_a_full[n1]);
+        }
+        if (lane == 0 && qt == 0) TCT(0, nt, 4 + j);
       }
-      mbar_arrive(&bar_raw_empty);  // this thread is done reading the raw tile
-      ++nt;
-    }
-  } else if (warp < 8) {
-    // =========================================== EPILOGUE ===========================================
-    const int ew = warp - 4;                 // == warp % 4: TMEM lanes 32 ew .. 32 ew + 31
-    const int m = ew * 32 + lane;            // frame within the tile
-    const uint32_t tlane = tmem + ((uint32_t)(ew * 32) << 16);
-    uint32_t nt = 0;
-    for (uint32_t id = blockIdx.x; id < p.total_tiles; id += gridDim.x) {
-      const Tile t = tile_info(p, id);
-      if (t.mode == kModeSilent) continue;
-      const int t0 = t.tile * kTileM;
+      ks += kKSteps;
+      mbar_arrive(&bar_raw_empty[rb]);  // this thread is done reading the raw tile
+
+      // ---- epilogue phase ----
       const bool valid = t0 + m < kNFrames;
       OutT* const obase = reinterpret_cast<OutT*>(p.out) + (size_t)t.b * kNMel * kNFrames + t0 + m;
-      if (p.mask != nullptr && valid) p.mask[(size_t)t.b * kNFrames + t0 + m] = ((t0 + m) * kHop < t.len) ? 1 : 0;
-      if (m == 0) TCT(1, nt, 0);
+      if (hh == 0 && p.mask != nullptr && valid) p.mask[(size_t)t.b * kNFrames + t0 + m] = ((t0 + m) * kHop < t.len) ? 1 : 0;
+      if (wt == 0) TCT(1, nt, 0);
       mbar_wait(&bar_d_full, nt & 1u, err_flag);
       tc_fence_after();
-      if (m == 0) TCT(1, nt, 1);
-      const float tile_k = s_tilek[nt & 1u];
+      if (wt == 0) TCT(1, nt, 1);
       uint32_t rmax = 0u, rmin = 0x7f800000u;
       uint32_t q0[16], q1[16], q2[16], q3[16];
       f2 P0, P1, P2, P3;
 
-#define TC_LOAD(g)                                  \
-  tmem_ld16(tlane + 0 * kN + 16 * (g), q0);         \
-  tmem_ld16(tlane + 1 * kN + 16 * (g), q1);         \
-  tmem_ld16(tlane + 2 * kN + 16 * (g), q2);         \
-  tmem_ld16(tlane + 3 * kN + 16 * (g), q3);         \
+#define TC_LOAD(g, col)                         \
+  tmem_ld16(tlane + 0 * kN + (col), q0);        \
+  tmem_ld16(tlane + 1 * kN + (col), q1);        \
+  tmem_ld16(tlane + 2 * kN + (col), q2);        \
+  tmem_ld16(tlane + 3 * kN + (col), q3);        \
   tmem_ld_wait();
       // columns of pair i within the group: (re k2, re k2+1, im k2, im k2+1).  T_n1 = Y_n1 * (cos - i sin):
       //   re = yr c + yi s, im = yi c - yr s; then the 4-point DFT over n1 and the four powers
+#define TC_TWID(qq, i, pp, n1m1, outr, outi)                                                                \
+  {                                                                                                         \
+    const float4 w = tw_sm[(pp) * 3 + (n1m1)];                                                              \
+    const f2 yr = mk2(__uint_as_float(qq[4 * (i)]), __uint_as_float(qq[4 * (i) + 1]));                       \
+    const f2 yi = mk2(__uint_as_float(qq[4 * (i) + 2]), __uint_as_float(qq[4 * (i) + 3]));                   \
+    outr = vfma(yr, mk2(w.x, w.y), vmul(yi, mk2(w.z, w.w)));                                                \
+    outi = vfma(yi, mk2(w.x, w.y), -vmul(yr, mk2(w.z, w.w)));                                               \
+  }
 #define TC_PAIR(i, pp)                                                                                     \
   {                                                                                                        \
     const f2 y0r = mk2(__uint_as_float(q0[4 * (i)]), __uint_as_float(q0[4 * (i) + 1]));                     \
     const f2 y0i = mk2(__uint_as_float(q0[4 * (i) + 2]), __uint_as_float(q0[4 * (i) + 3]));                 \
-    f2 tr[3], ti[3];                                                                                       \
-    {                                                                                                      \
-      const float4 w = tw_sm[(pp) * 3 + 0];                                                                \
-      const f2 yr = mk2(__uint_as_float(q1[4 * (i)]), __uint_as_float(q1[4 * (i) + 1]));                    \
-      const f2 yi = mk2(__uint_as_float(q1[4 * (i) + 2]), __uint_as_float(q1[4 * (i) + 3]));                \
-      tr[0] = vfma(yr, mk2(w.x, w.y), vmul(yi, mk2(w.z, w.w)));                                            \
-      ti[0] = vfma(yi, mk2(w.x, w.y), -vmul(yr, mk2(w.z, w.w)));                                           \
-    }                                                                                                      \
-    {                                                                                                      \
-      const float4 w = tw_sm[(pp) * 3 + 1];                                                                \
-      const f2 yr = mk2(__uint_as_float(q2[4 * (i)]), __uint_as_float(q2[4 * (i) + 1]));                    \
-      const f2 yi = mk2(__uint_as_float(q2[4 * (i) + 2]), __uint_as_float(q2[4 * (i) + 3]));                \
-      tr[1] = vfma(yr, mk2(w.x, w.y), vmul(yi, mk2(w.z, w.w)));                                            \
-      ti[1] = vfma(yi, mk2(w.x, w.y), -vmul(yr, mk2(w.z, w.w)));                                           \
-    }                                                                                                      \
-    {                                                                                                      \
-      const float4 w = tw_sm[(pp) * 3 + 2];                                                                \
-      const f2 yr = mk2(__uint_as_float(q3[4 * (i)]), __uint_as_float(q3[4 * (i) + 1]));                    \
-      const f2 yi = mk2(__uint_as_float(q3[4 * (i) + 2]), __uint_as_float(q3[4 * (i) + 3]));                \
-      tr[2] = vfma(yr, mk2(w.x, w.y), vmul(yi, mk2(w.z, w.w)));                                            \
-      ti[2] = vfma(yi, mk2(w.x, w.y), -vmul(yr, mk2(w.z, w.w)));                                           \
-    }                                                                                                      \
-    const f2 s02r = y0r + tr[1], s02i = y0i + ti[1], d02r = y0r - tr[1], d02i = y0i - ti[1];               \
-    const f2 s13r = tr[0] + tr[2], s13i = ti[0] + ti[2], d13r = tr[0] - tr[2], d13i = ti[0] - ti[2];       \
+    f2 t1r, t1i, t2r, t2i, t3r, t3i;                                                                       \
+    TC_TWID(q1, i, pp, 0, t1r, t1i)                                                                        \
+    TC_TWID(q2, i, pp, 1, t2r, t2i)                                                                        \
+    TC_TWID(q3, i, pp, 2, t3r, t3i)                                                                        \
+    const f2 s02r = y0r + t2r, s02i = y0i + t2i, d02r = y0r - t2r, d02i = y0i - t2i;                       \
+    const f2 s13r = t1r + t3r, s13i = t1i + t3i, d13r = t1r - t3r, d13i = t1i - t3i;                       \
     const f2 x0r = s02r + s13r, x0i = s02i + s13i, x2r = s02r - s13r, x2i = s02i - s13i;                   \
     const f2 x1r = d02r + d13i, x1i = d02i - d13r, x3r = d02r - d13i, x3i = d02i + d13r;                   \
     P0 = vfma(x0r, x0r, vmul(x0i, x0i));                                                                   \
@@ -552,9 +678,13 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_tc_kernel(const TcParams p
 #define TC_RELEASE()         \
   tc_fence_before();         \
   mbar_arrive(&bar_d_empty); \
-  if (m == 0) TCT(1, nt, 2);
+  if (wt == 0) TCT(1, nt, 2);
 #define TC_ACC_SET(mm, pexpr, wbits) float a_##mm = (pexpr) * __uint_as_float(wbits);
 #define TC_ACC(mm, pexpr, wbits) a_##mm = fmaf((pexpr), __uint_as_float(wbits), a_##mm);
+#define TC_PART_PUT(slot, mm) s_part[(slot) * kTileM + m] = a_##mm;
+#define TC_PART_SIGNAL() asm volatile("bar.arrive %0, 64;" ::"r"(2 + qt) : "memory");
+#define TC_PART_WAIT() asm volatile("bar.sync %0, 64;" ::"r"(2 + qt) : "memory");
+#define TC_PART_GET(slot, mm) a_##mm += s_part[(slot) * kTileM + m];
 #define TC_FIN_ZERO(mm) \
   float a_##mm = 0.f;   \
   TC_FIN(mm)
@@ -575,21 +705,26 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_tc_kernel(const TcParams p
       }
 #undef WFE_TC_GEN_NMEL
 #undef TC_LOAD
+#undef TC_TWID
 #undef TC_PAIR
 #undef TC_RELEASE
 #undef TC_ACC_SET
 #undef TC_ACC
+#undef TC_PART_PUT
+#undef TC_PART_SIGNAL
+#undef TC_PART_WAIT
+#undef TC_PART_GET
 #undef TC_FIN
 #undef TC_FIN_ZERO
       // ---- tile extrema (raw scaled mel powers, >= 0: uint order == float order) -> clamp warp ----
-      if (m == 0) TCT(1, nt, 3);
+      if (wt == 0) TCT(1, nt, 3);
       rmax = __reduce_max_sync(0xffffffffu, rmax);
       rmin = __reduce_min_sync(0xffffffffu, rmin);
       mbar_wait(&bar_st_empty[nt & 1u], ((nt >> 1) & 1u) ^ 1u, err_flag);
       __syncwarp();
       if (lane == 0) {
-        s_red[nt & 1u][0][ew] = fmaf(lg2_approx(__uint_as_float(rmax)), 0.25f * kLog10_2, tile_k);
-        s_red[nt & 1u][1][ew] = fmaf(lg2_approx(__uint_as_float(rmin)), 0.25f * kLog10_2, tile_k);
+        s_red[nt & 1u][0][warp] = fmaf(lg2_approx(__uint_as_float(rmax)), 0.25f * kLog10_2, tile_k);
+        s_red[nt & 1u][1][warp] = fmaf(lg2_approx(__uint_as_float(rmin)), 0.25f * kLog10_2, tile_k);
         __threadfence_block();
         mbar_arrive(&bar_st_full[nt & 1u]);  // release: the tile's global stores (ordered by __syncwarp) and s_red
       }
@@ -597,42 +732,41 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_tc_kernel(const TcParams p
     }
   } else if (warp == 8) {
     // =========================================== MMA ISSUER ===========================================
-    if (lane == 0) {
-      // descriptors differ only in the start address: add (byte offset >> 4) to the low word (addresses < 256 KB)
-      const uint64_t a_desc0 = smem_desc(smem_u32(a_ring), kChunkBytes, 128);
-      const uint64_t b_desc0 = smem_desc(smem_u32(b_sm), kBChunkBytes, 128);
-      uint32_t ks = 0, nt = 0;
-      for (uint32_t id = blockIdx.x; id < p.total_tiles; id += gridDim.x) {
-        const Tile t = tile_info(p, id);
-        if (t.mode == kModeSilent) continue;
-        TCT(2, nt, 0);
-        mbar_wait(&bar_d_empty, (nt & 1u) ^ 1u, err_flag);  // epilogue has drained the previous tile's accumulators
-        tc_fence_after();
-        TCT(2, nt, 1);
+    // The whole warp walks the loop (waits included); one elected lane issues the tensor-core instructions.
+    // B descriptors differ only in the start address: add (byte offset >> 4) to the low word (addresses < 256 KB)
+    const uint64_t b_desc0 = smem_desc(smem_u32(b_sm), kBChunkBytes, 128);
+    uint32_t ks = 0, nt = 0;
+    for (uint32_t id = blockIdx.x; id < p.total_tiles; id += gridDim.x) {
+      const Tile t = tile_info(p, id);
+      if (t.mode == kModeSilent) continue;
+      if (lane == 0) TCT(2, nt, 0);
+      mbar_wait(&bar_d_empty, (nt & 1u) ^ 1u, err_flag);  // epilogue has drained the previous tile's accumulators
+      tc_fence_after();
+      if (lane == 0) TCT(2, nt, 1);
 #pragma unroll 1
-        for (int j = 0; j < kKSteps; ++j, ++ks) {
-          const uint32_t stage = ks & 1u;
-          mbar_wait(&bar_a_full[stage], (ks >> 1) & 1u, err_flag);
-          tc_fence_after();
-          const uint64_t sa = a_desc0 + (uint64_t)((stage * kStageBytes) >> 4);
-          const uint64_t bh = b_desc0 + (uint64_t)(((uint32_t)(2 * j) * kBChunkBytes) >> 4);
-          const uint64_t bl = bh + (uint64_t)((kBBytes / 2) >> 4);
-          const uint32_t acc = j > 0 ? 1u : 0u;
+      for (int j = 0; j < kKSteps; ++j, ++ks) {
+        const uint64_t bh = b_desc0 + (uint64_t)(((uint32_t)(2 * j) * kBChunkBytes) >> 4);
+        const uint64_t bl = bh + (uint64_t)((kBBytes / 2) >> 4);
+        const uint32_t acc = j > 0 ? 1u : 0u;
 #pragma unroll
-          for (int n1 = 0; n1 < 4; ++n1) {
-            const uint64_t ah = sa + (uint64_t)((((n1 * 2 + 0) * 2) * kChunkBytes) >> 4);
-            const uint64_t al = sa + (uint64_t)((((n1 * 2 + 1) * 2) * kChunkBytes) >> 4);
+        for (int n1 = 0; n1 < 4; ++n1) {
+          mbar_wait(&bar_a_full[n1], ks & 1u, err_flag);
+          tc_fence_after();
+          if (elect_one()) {
             const uint32_t d = tmem + (uint32_t)(n1 * kN);
-            mma_f16(d, ah, bh, kIdesc, acc);
-            mma_f16(d, ah, bl, kIdesc, 1u);
-            mma_f16(d, al, bh, kIdesc, 1u);
+            const uint32_t ah = tmem + (uint32_t)(kTmemA + 16 * n1), al = ah + 8;
+            mma_f16_ts(d, ah, bh, kIdesc, acc);
+            mma_f16_ts(d, ah, bl, kIdesc, 1u);
+            mma_f16_ts(d, al, bh, kIdesc, 1u);
+            mma_commit(&bar_a_empty[ks & 1u][n1]);  // implies tcgen05.fence::before_thread_sync
           }
-          mma_commit(&bar_a_empty[stage]);  // implies tcgen05.fence::before_thread_sync
-          TCT(2, nt, 2 + j);
+          __syncwarp();
         }
-        mma_commit(&bar_d_full);
-        ++nt;
+        if (lane == 0) TCT(2, nt, 2 + j);
       }
+      if (elect_one()) mma_commit(&bar_d_full);
+      __syncwarp();
+      ++nt;
     }
   } else if (warp == 9) {
     // =========================================== LOADER ===========================================
@@ -640,20 +774,20 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_tc_kernel(const TcParams p
     for (uint32_t id = blockIdx.x; id < p.total_tiles; id += gridDim.x) {
       const Tile t = tile_info(p, id);
       if (t.mode == kModeSilent) continue;
+      const uint32_t rb = nt & 1u;
       if (lane == 0) TCT(3, nt, 0);
-      mbar_wait(&bar_raw_empty, (nt & 1u) ^ 1u, err_flag);  // prep has finished reading the previous raw tile
+      mbar_wait(&bar_raw_empty[rb], ((nt >> 1) & 1u) ^ 1u, err_flag);  // prep has finished with this buffer's previous tile
       if (lane == 0) TCT(3, nt, 1);
-      if (t.mode == kModeAsync) {
-        const float* src = reinterpret_cast<const float*>(p.pcm) + t.off + (t.tile * kTileM * kHop - kNFft / 2);
-        if (lane == 0) mbar_arrive_expect_tx(&bar_raw_full, kRawLen * 4);
-        __syncwarp();
-        for (int r = lane; r < kRawRows; r += 32) {
-          const uint32_t bytes = (r < kRawRows - 1) ? kHop * 4 : (kRawLen - (kRawRows - 1) * kHop) * 4;
-          bulk_g2s(raw + r * kRawPitch, src + r * kHop, bytes, &bar_raw_full);
+      if (elect_one()) {
+        if (t.mode == kModeAsync || t.mode == kModeAsyncHead) {
+          mbar_arrive_expect_tx(&bar_raw_full[rb], kRawBoxBytes);
+          tma_load_2d(smem + kSmemRaw + rb * kRawBufBytes, &tmap,
+                      (int32_t)(t.off + (int64_t)(t.tile * kTileM * kHop - kNFft / 2)), 0, &bar_raw_full[rb]);
+        } else {
+          mbar_arrive(&bar_raw_full[rb]);  // generic staging: the prep warps fill the buffer themselves
         }
-      } else if (lane == 0) {
-        mbar_arrive(&bar_raw_full);  // generic staging: the prep warps fill the buffer themselves
       }
+      __syncwarp();
       if (lane == 0) TCT(3, nt, 2);
       ++nt;
     }
@@ -676,9 +810,14 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_tc_kernel(const TcParams p
         }
       } else {
         mbar_wait(&bar_st_full[nt & 1u], (nt >> 1) & 1u, err_flag);
-        // an epilogue warp whose 32 frames lie beyond frame 3000 reports the identities (lg2(0) = -inf, lg2(inf) = +inf)
-        mx = fmaxf(fmaxf(s_red[nt & 1u][0][0], s_red[nt & 1u][0][1]), fmaxf(s_red[nt & 1u][0][2], s_red[nt & 1u][0][3]));
-        mn = fminf(fminf(s_red[nt & 1u][1][0], s_red[nt & 1u][1][1]), fminf(s_red[nt & 1u][1][2], s_red[nt & 1u][1][3]));
+        // a worker warp whose 32 frames lie beyond frame 3000 reports the identities (lg2(0) = -inf, lg2(inf) = +inf)
+        mx = -__int_as_float(0x7f800000);
+        mn = __int_as_float(0x7f800000);
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+          mx = fmaxf(mx, s_red[nt & 1u][0][w]);
+          mn = fminf(mn, s_red[nt & 1u][1][w]);
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_st_empty[nt & 1u]);
         ++nt;
@@ -729,6 +868,14 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_tc_kernel(const TcParams p
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
+#ifdef WFE_TC_TRACE
+  if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 77)) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    g_tc_trace[(4 + (blockIdx.x ? 5 : 0)) * kTrPts + 2] = clock64();
+    g_tc_trace[(4 + (blockIdx.x ? 5 : 0)) * kTrPts + 3] = gt;
+  }
+#endif
   if (warp == 9) tmem_dealloc(tmem, kTmemCols);
 }
 

@@ -63,43 +63,76 @@ def schedule():
 
 
 def emit(n_mel: int, w: np.ndarray, out: list) -> None:
+    """Two instruction streams, one per epilogue half (two warps share the 32 frames of a TMEM lane quarter):
+    half 0 handles k2 pairs 0..12, half 1 pairs 13..25.  A filter fed by both halves is OWNED by half 0; half 1 meets
+    those filters in its FIRST pairs (the four fronts cross the half boundary there), parks the partial sums in shared
+    memory (TC_PART_PUT) and signals; half 0 picks them up after its own last pair (TC_PART_GET) -- it never waits."""
     order = schedule()
+    half_of = lambda p: 0 if p < 13 else 1
     nz = {b: [m for m in range(n_mel) if w[b, m] != 0.0] for b in range(201)}
-    last_time = {}
-    first_time = {}
-    for t, (_, _, _, b) in enumerate(order):
-        for m in nz[b]:
-            last_time[m] = t
-            first_time.setdefault(m, t)
-    empty = [m for m in range(n_mel) if m not in first_time]
-    out.append(f"#if !defined(WFE_TC_GEN_HOST_TABLES) && WFE_TC_GEN_NMEL == {n_mel}")
-    out.append(f"// ---- {n_mel} mel: {sum(len(v) for v in nz.values())} non-zeros, {len(empty)} empty filters ----")
-    for m in empty:
-        out.append(f"TC_FIN_ZERO({m})")
-    t = 0
-    cur_pair = -1
+    halves_of_mel = {m: set() for m in range(n_mel)}
     for (p, e, f, b) in order:
-        if p != cur_pair:
-            if p % 4 == 0:
-                g = p // 4
-                out.append(f"TC_LOAD({g})")
-            out.append(f"TC_PAIR({p % 4}, {p})")
-            cur_pair = p
-            if p == 25:
-                out.append("TC_RELEASE()  // last TMEM read done: the accumulators may be overwritten")
-        comp = "x" if e == 0 else "y"
         for m in nz[b]:
-            wb = bits(w[b, m])
-            if first_time[m] == t:
-                out.append(f"TC_ACC_SET({m}, P{f}.v.{comp}, 0x{wb:08x}u)  // bin {b}")
-            else:
-                out.append(f"TC_ACC({m}, P{f}.v.{comp}, 0x{wb:08x}u)  // bin {b}")
-            if last_time[m] == t:
+            halves_of_mel[m].add(half_of(p))
+    shared = sorted(m for m in range(n_mel) if halves_of_mel[m] == {0, 1})
+    slot_of = {m: i for i, m in enumerate(shared)}
+    empty = [m for m in range(n_mel) if not halves_of_mel[m]]
+    out.append(f"#if !defined(WFE_TC_GEN_HOST_TABLES) && !defined(WFE_TC_GEN_WINDOW) && !defined(WFE_TC_GEN_COUNTS) && WFE_TC_GEN_NMEL == {n_mel}")
+    out.append(f"// ---- {n_mel} mel: {sum(len(v) for v in nz.values())} non-zeros, {len(empty)} empty filters, "
+               f"{len(shared)} filters fed by both halves: {shared} ----")
+    for hh in (0, 1):
+        out.append(f"if (hh == {hh}) {{")
+        seq = [(p, e, f, b) for (p, e, f, b) in order if half_of(p) == hh]
+        first_time, last_time = {}, {}
+        for t, (_, _, _, b) in enumerate(seq):
+            for m in nz[b]:
+                last_time[m] = t
+                first_time.setdefault(m, t)
+        if hh == 0:
+            for m in empty:
+                out.append(f"TC_FIN_ZERO({m})")
+        pairs = sorted({p for (p, _, _, _) in seq})
+        cur_pair, t = -1, 0
+        pending_put = [m for m in shared] if hh == 1 else []
+        for (p, e, f, b) in seq:
+            if p != cur_pair:
+                i = pairs.index(p)
+                if i % 4 == 0:
+                    out.append(f"TC_LOAD({i // 4}, {4 * p})")  # group index, first TMEM column of the group
+                out.append(f"TC_PAIR({i % 4}, {p})")
+                cur_pair = p
+                if p == pairs[-1]:
+                    out.append("TC_RELEASE()  // this thread's last TMEM read is done")
+            comp = "x" if e == 0 else "y"
+            for m in nz[b]:
+                wb = bits(w[b, m])
+                if first_time[m] == t:
+                    out.append(f"TC_ACC_SET({m}, P{f}.v.{comp}, 0x{wb:08x}u)  // bin {b}")
+                else:
+                    out.append(f"TC_ACC({m}, P{f}.v.{comp}, 0x{wb:08x}u)  // bin {b}")
+                if last_time[m] == t:
+                    if m in slot_of:
+                        if hh == 1:
+                            out.append(f"TC_PART_PUT({slot_of[m]}, {m})")
+                            pending_put.remove(m)
+                            if not pending_put:
+                                out.append("TC_PART_SIGNAL()  // every partial sum is parked: wake half 0")
+                        # half 0 finishes shared filters after the exchange (below)
+                    else:
+                        out.append(f"TC_FIN({m})")
+            t += 1
+        if hh == 0 and shared:
+            out.append("TC_PART_WAIT()")
+            for m in shared:
+                out.append(f"TC_PART_GET({slot_of[m]}, {m})")
                 out.append(f"TC_FIN({m})")
-        t += 1
+        out.append("}")
+    out.append("#endif")
+    out.append(f"#if defined(WFE_TC_GEN_COUNTS) && WFE_TC_GEN_NMEL == {n_mel}")
+    out.append(f"constexpr int kTcShared{n_mel} = {len(shared)};")
     out.append("#endif")
     # host-side check table
-    out.append(f"#if defined(WFE_TC_GEN_HOST_TABLES) && WFE_TC_GEN_NMEL == {n_mel}")
+    out.append(f"#if defined(WFE_TC_GEN_HOST_TABLES) && !defined(WFE_TC_GEN_WINDOW) && WFE_TC_GEN_NMEL == {n_mel}")
     trip = [(b, m, bits(w[b, m])) for b in range(201) for m in nz[b]]
     out.append(f"static const uint32_t kTcNnz{n_mel}[{len(trip)}][3] = {{")
     for i in range(0, len(trip), 6):
@@ -108,9 +141,23 @@ def emit(n_mel: int, w: np.ndarray, out: list) -> None:
     out.append("#endif")
 
 
+def emit_window(out: list) -> None:
+    """Periodic Hann window (HF:audio_utils.py:593-607 == torch.hann_window(400)) as fp32 literals: with the prep loop
+    fully unrolled every window factor becomes an FMUL immediate."""
+    n = np.arange(400, dtype=np.float64)
+    w = (0.5 - 0.5 * np.cos(2.0 * np.pi * n / 400.0)).astype(np.float32)
+    out.append("#if defined(WFE_TC_GEN_WINDOW)")
+    out.append("__device__ constexpr uint32_t kWinBits[400] = {")
+    for i in range(0, 400, 8):
+        out.append("  " + " ".join(f"0x{bits(x):08x}u," for x in w[i:i + 8]))
+    out.append("};")
+    out.append("#endif")
+
+
 def main() -> int:
     out = ["// GENERATED by tools/gen_tc_epilogue.py -- do not edit.  Straight-line mel epilogue of wfe::tc::logmel_tc_kernel.",
            "// Include with WFE_TC_GEN_NMEL = 80 or 128 and the TC_* macros defined (see wfe_logmel_tc.cuh)."]
+    emit_window(out)
     for n_mel in (80, 128):
         emit(n_mel, filter_bank(n_mel), out)
     with open(OUT, "w") as f:

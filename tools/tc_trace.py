@@ -24,11 +24,15 @@ for _ in range(2):
     fe.logmel_device(pcm, offs, B, out=out)
 torch.cuda.synchronize()
 lib = pkg._lib.load()
-T, R, P = 8, 5, 16
+T, R, P = 8, 5, 32
 buf = np.zeros(T * R * P, dtype=np.uint64)
 rc = lib.wfe_debug_read_tc_trace(buf.ctypes.data_as(C.c_void_p), buf.size)
 assert rc == 0, rc
 tr = buf.reshape(T, R, P).astype(np.int64)
+for it_, name in ((0, "CTA 0"), (1, "CTA 77")):
+    c0, g0, c1, g1 = [int(x) for x in tr[it_, 4, :4]]
+    print(f"{name}: kernel span {c1 - c0} SM cycles, {g1 - g0} ns -> {(c1 - c0) / max(g1 - g0, 1):.3f} GHz")
+tr[:, 4, :] = 0
 t0 = tr[tr > 0].min()
 names = {0: "prep  [start wait_raw, raw ok, staged, scaled, k0..k6 done]", 1: "epi   [start wait_d, d ok, released, done]",
          2: "mma   [start wait_dempty, ok, k0..k6 issued]", 3: "load  [start wait_rawempty, ok, issued]"}
@@ -36,5 +40,8 @@ for it in range(T):
     print(f"--- tile iteration {it + 4} (CTA 0; tile ids 0+148*it: tile-in-clip {(148 * (it + 4)) % 24}) ---")
     for r in range(4):
         v = tr[it, r]
-        pts = [int(x - t0) for x in v if x > 0]
+        pts = [int(x - t0) for x in v[:16] if x > 0]
         print(f"  {names[r]:60s} {pts}")
+        fine = [int(x - t0) for x in v[16:] if x > 0]
+        if fine:
+            print(f"      k-step 3 detail (prep: compute done, then per slot [empty ok, st done, arrived]; mma: per slot [start wait, full ok, committed]): {fine}")
