@@ -72,7 +72,7 @@ constexpr int kTwBytes = 26 * 3 * 16;             // [pair][n1-1] (cos_k2, cos_k
 constexpr int kThreads = 11 * 32;
 constexpr int kTmemCols = 512;
 constexpr int kTmemA = 4 * kN;                    // columns 448..511: A slots, 16 columns per n1 (8 hi + 8 lo)
-constexpr int kRing = 128;
+constexpr int kRing = 16;   // pending-tile ring of the clamp warp (a clip completes within about one tile iteration)
 constexpr int kRawBoxBytes = kRawRows * kRawPitch * 4;              // 85280: what one TMA delivers
 constexpr int kRawBufBytes = (kRawBoxBytes + 127) & ~127;           // 85376: TMA destinations are 128-byte aligned
 
@@ -80,7 +80,8 @@ constexpr size_t kSmemRaw = 0;
 constexpr size_t kSmemB = kSmemRaw + 2 * (size_t)kRawBufBytes;       // 170752
 constexpr size_t kSmemTw = kSmemB + kBBytes;                         // +50176
 constexpr size_t kSmemWs = kSmemTw + kTwBytes;                       // scaled window, 7 x 64 entries (zero beyond 400)
-constexpr size_t kSmemBytes = kSmemWs + kKSteps * 64 * 4;            // 223968
+constexpr int kWsFloats = kKSteps * 64;                              // 448
+constexpr size_t kSmemBytes = kSmemWs + 2 * kWsFloats * 4;           // 225760 (+ ~4.2 KB static: the 227 KB of an SM)
 
 #define WFE_TC_GEN_WINDOW 1
 #include "wfe_tc_epilogue_gen.inc"
@@ -157,6 +158,9 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+#ifndef WFE_TC_DEPOSIT
+#define WFE_TC_DEPOSIT 0  // operand slots handed over one by one (0) or in two groups of two (1)
+#endif
 #ifndef WFE_TC_WAIT
 #define WFE_TC_WAIT 1  // 0: bare try_wait spin, 1: try_wait with a suspend-time hint, 2: nanosleep back-off between polls
 #endif
@@ -262,6 +266,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor): LBO = byte distance between the two
 // 8-element K chunks of one MMA, SBO = byte distance between 8-row core matrices (128: rows are contiguous 16-byte units)
@@ -281,7 +291,7 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
 // ---------------------------------------------------------------------------------------------------------------
 // tile geometry: every role derives it from the tile id alone
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kModeAsyncHead = 3;
+constexpr int kModeAsyncHead = 3, kModeDone = -1;
 struct Tile {
   int b, tile, len, mode;  // mode: kModeSilent / kModeAsync (TMA) / kModeAsyncHead (TMA + reflect patch) / kModeSync (generic)
   int64_t off;
@@ -349,7 +359,7 @@ __device__ __forceinline__ void fix_tile_tc(OutT* __restrict__ out, int n_mel, i
 #pragma unroll
   for (int e = 0; e < 4; ++e) cv[e] = to_out<OutT>(fl);
   const Vec cvec = *reinterpret_cast<const Vec*>(cv);
-  constexpr int kDeep = 8;
+  constexpr int kDeep = 16;  // rows in flight: one warp has to keep up with a fix-up per tile on speech-like audio
   for (int m0 = 0; m0 < n_mel; m0 += kDeep) {
     if (silent) {
 #pragma unroll
@@ -391,6 +401,65 @@ __device__ __forceinline__ float wait_clip_floor_tc(const uint32_t* tile_key, in
   }
 }
 
+// what the loader warp hands to the workers with each raw tile
+struct alignas(16) TileMeta {
+  int32_t b, tile, len, mode;  // mode kModeDone: no more tiles
+  int64_t off;
+  float scale, tile_k;         // power-of-two scale of the tile; y = lg2(mel_scaled) * C + tile_k
+};
+// scale = 2^(14 - e), e = unbiased exponent of the tile maximum (clamped so that the scale stays a normal float);
+// y = (log10(mel_scaled * 2^(-2 (14 - e))) + 4) / 4 = lg2(mel_scaled) * C + (1 - 2 (14 - e) C)
+__device__ __forceinline__ void scale_from_max(uint32_t mx_bits, float& scale, float& tile_k) {
+  int e = (int)((mx_bits >> 23) & 0xffu) - 127;
+  if (mx_bits == 0u) e = 14;
+  e = max(-100, min(e, 100));
+  scale = __uint_as_float((uint32_t)(127 + 14 - e) << 23);
+  tile_k = 1.0f - (float)(2 * (14 - e)) * (0.25f * kLog10_2);
+}
+// max |x| over a staged raw tile, as float bits, by `nthreads` cooperating threads (thread index t): thread t scans hop
+// rows t, t + nthreads, ... (row pitch 164 words: conflict-free LDS.128 across lanes), ten loads in flight
+__device__ __forceinline__ uint32_t raw_absmax(const float* raw, int t, int nthreads) {
+  float mx = 0.f;
+  for (int r = t; r < kRawRows; r += nthreads) {
+    const float4* row = reinterpret_cast<const float4*>(raw + r * kRawPitch);
+    const int n4 = r == kRawRows - 1 ? (kRawLen - (kRawRows - 1) * kHop) / 4 : kHop / 4;  // the last row is half a row
+#pragma unroll
+    for (int c0 = 0; c0 < kHop / 4; c0 += 10) {
+      float4 v[10];
+#pragma unroll
+      for (int u = 0; u < 10; ++u) v[u] = row[c0 + u];
+#pragma unroll
+      for (int u = 0; u < 10; ++u)
+        if (c0 + u < n4) mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v[u].x), fabsf(v[u].y)), fmaxf(fabsf(v[u].z), fabsf(v[u].w))));
+    }
+  }
+  return __float_as_uint(mx);
+}
+// the same for float4 elements i = t + nthreads * u, u in [u0, u1): slices that the workers fit between their k-steps
+__device__ __forceinline__ float raw_absmax_slice(const float* raw, int t, int nthreads, int u0, int u1) {
+  float mx = 0.f;
+  constexpr int kQuads = ((kRawRows - 1) * kHop + (kRawLen - (kRawRows - 1) * kHop)) / 4;  // 5180 float4 of real samples
+#pragma unroll
+  for (int u = u0; u < u1; ++u) {
+    const int i = t + nthreads * u;
+    if (i < kQuads) {
+      const int r = i / (kHop / 4);
+      const float4 v = *reinterpret_cast<const float4*>(raw + r * kRawPitch + 4 * (i - r * (kHop / 4)));
+      mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+  }
+  return mx;
+}
+// scaled window table (exact: the scale is a power of two), zero beyond the 400-point frame
+__device__ __forceinline__ void write_ws(float* ws, float scale, int t, int nthreads) {
+  for (int i = t; i < kWsFloats / 4; i += nthreads) {
+    uint4 w = make_uint4(0u, 0u, 0u, 0u);
+    if (4 * i < kNFft) w = __ldg(reinterpret_cast<const uint4*>(kWinBits) + i);  // (no shared memory left for a copy)
+    reinterpret_cast<float4*>(ws)[i] = make_float4(__uint_as_float(w.x) * scale, __uint_as_float(w.y) * scale,
+                                                   __uint_as_float(w.z) * scale, __uint_as_float(w.w) * scale);
+  }
+}
+
 // named barrier among the 256 worker threads
 __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
@@ -403,14 +472,16 @@ __global__ void __launch_bounds__(kThreads, 1)
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* const b_sm = smem + kSmemB;
   const float4* const tw_sm = reinterpret_cast<const float4*>(smem + kSmemTw);
-  float* const ws = reinterpret_cast<float*>(smem + kSmemWs);
+  float* const ws_sm = reinterpret_cast<float*>(smem + kSmemWs);  // [2 raw buffers][448]
 
-  __shared__ uint64_t bar_raw_full[2], bar_raw_empty[2], bar_a_full[4], bar_a_empty[2][4], bar_d_full, bar_d_empty,
-      bar_st_full[2], bar_st_empty[2];
+  __shared__ uint64_t bar_raw_full[2], bar_raw_empty[2], bar_meta_full[2], bar_a_full[4], bar_a_empty[2][4], bar_d_full,
+      bar_d_empty, bar_st_full[2], bar_st_empty[2];
+  __shared__ TileMeta s_meta[2];        // loader -> workers: geometry, scale and log-domain constant of the tile in buffer rb
   __shared__ uint32_t s_tmem;
-  __shared__ uint32_t s_pmax[8];        // prep: per-warp max |x| bits
+  __shared__ uint32_t s_pmax[8];        // generic staging: per-warp max |x| bits
+  __shared__ uint32_t s_tilemax[2];     // per raw buffer: max |x| bits of the tile (atomicMax by the worker warps)
   __shared__ float s_red[2][2][8];      // [tile parity][max, min][worker warp] of y over the warp's share of the tile
-  __shared__ float s_part[kMaxShared * kTileM];  // epilogue half 1 -> half 0: partial sums of the shared mel filters
+  __shared__ float s_part[(kNMel == 128 ? kTcShared128 : kTcShared80) * kTileM];  // epilogue half 1 -> half 0: partial sums of the shared mel filters
   __shared__ int2 s_pend_bt[kRing];
   __shared__ float2 s_pend_mm[kRing];
 
@@ -433,6 +504,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bar_raw_full[s], 1);
       mbar_init(&bar_raw_empty[s], 256);
+      mbar_init(&bar_meta_full[s], 1);
       mbar_init(&bar_st_full[s], 8);
       mbar_init(&bar_st_empty[s], 1);
     }
@@ -443,6 +515,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     mbar_init(&bar_d_full, 1);
     mbar_init(&bar_d_empty, 256);
+    s_tilemax[0] = s_tilemax[1] = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 9) tmem_alloc(&s_tmem, kTmemCols);
@@ -459,195 +532,223 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int wt = tid;                      // 0..255 among the workers
     const uint32_t tlane = tmem + ((uint32_t)(qt * 32) << 16);
     const uint32_t a_slot0 = tlane + kTmemA;
-    uint32_t ks = 0;   // running k-step count
-    uint32_t nt = 0;   // running count of non-silent tiles
-    for (uint32_t id = blockIdx.x; id < p.total_tiles; id += gridDim.x) {
-      const Tile t = tile_info(p, id);
-      if (t.mode == kModeSilent) continue;
-      const uint32_t rb = nt & 1u;
+
+    // receive the tile in raw buffer (n & 1): geometry + scale from the loader; tiles that need the generic staging
+    // path (clip edges, 2-byte PCM, normalisation) are staged, scanned and scaled here, by all workers
+    auto fetch = [&](uint32_t n, TileMeta& tm) {
+      const uint32_t rb = n & 1u;
+      mbar_wait(&bar_meta_full[rb], (n >> 1) & 1u, err_flag);
+      tm = s_meta[rb];
+      if (tm.mode != kModeSync) return;
       float* const raw = reinterpret_cast<float*>(smem + kSmemRaw + rb * kRawBufBytes);
-      const float* const xrow = raw + m * kRawPitch;
-      const int t0 = t.tile * kTileM;
+      const int t0 = tm.tile * kTileM;
       const int s_begin = t0 * kHop - kNFft / 2;
-      if (wt == 0) TCT(0, nt, 0);
-      mbar_wait(&bar_raw_full[rb], (nt >> 1) & 1u, err_flag);
-      if (wt == 0) TCT(0, nt, 1);
-      if (t.mode == kModeAsyncHead) {
-        // first tile of a clip: the TMA started 200 samples before the clip; replace them by the centred reflect pad
-        if (wt < kNFft / 2) {
-          const int s = kNFft / 2 - wt;  // raw[i] = x[200 - i]
-          raw[wt + (wt >= kHop ? kRawPitch - kHop : 0)] = s < t.len ? load_pcm(p.pcm, p.pcm_dtype, t.off + s, p.pcm_scale) : 0.f;
-        }
-        worker_bar();
-      } else if (t.mode == kModeSync) {
-        // generic staging: truncate / right-zero-pad to 30 s, centred reflect pad, dtype conversion, normalisation.
-        // Only the rows the tile's valid frames read; quads of samples, eight quads in flight per thread.
-        const int nvalid = min(kTileM, kNFrames - t0);
-        const int n_quads = ((nvalid - 1) * kHop + kNFft + 3) / 4;
-        float mean = 0.f, rstd = 1.f;
-        if (p.norm != nullptr) {
-          const float2 st = __ldg(p.norm + t.b);
-          mean = st.x;
-          rstd = st.y;
-        }
-        const bool vec_ok = (p.pcm_dtype == 0 || p.pcm_dtype == 3) &&
-                            ((reinterpret_cast<uintptr_t>(reinterpret_cast<const float*>(p.pcm) + t.off + s_begin) & 15u) == 0);
-        constexpr int kBatch = 8;
-        for (int g0 = wt; g0 < n_quads; g0 += 256 * kBatch) {
-          float4 v[kBatch];
+      const int nvalid = min(kTileM, kNFrames - t0);
+      const int n_quads = ((nvalid - 1) * kHop + kNFft + 3) / 4;  // only the rows the tile's valid frames read
+      float mean = 0.f, rstd = 1.f;
+      if (p.norm != nullptr) {
+        const float2 st = __ldg(p.norm + tm.b);
+        mean = st.x;
+        rstd = st.y;
+      }
+      const bool vec_ok = (p.pcm_dtype == 0 || p.pcm_dtype == 3) &&
+                          ((reinterpret_cast<uintptr_t>(reinterpret_cast<const float*>(p.pcm) + tm.off + s_begin) & 15u) == 0);
+      constexpr int kBatch = 8;  // quads of samples in flight per thread
+      for (int g0 = wt; g0 < n_quads; g0 += 256 * kBatch) {
+        float4 v[kBatch];
 #pragma unroll
-          for (int u = 0; u < kBatch; ++u) {
-            const int i = 4 * (g0 + 256 * u);
-            const int s = s_begin + i;
-            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (g0 + 256 * u < n_quads) {
-              if (vec_ok && s >= 0 && s + 3 < t.len) {  // interior (t.len <= n_samples: no reflection either)
-                v[u] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.pcm) + t.off + s));
-              } else {
-                float e[4];
+        for (int u = 0; u < kBatch; ++u) {
+          const int s = s_begin + 4 * (g0 + 256 * u);
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (g0 + 256 * u < n_quads) {
+            if (vec_ok && s >= 0 && s + 3 < tm.len) {  // interior (len <= n_samples: no reflection either)
+              v[u] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.pcm) + tm.off + s));
+            } else {
+              float e[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  int sk = s + k;
-                  if (sk < 0) sk = -sk;
-                  if (sk >= kNSamples) sk = 2 * (kNSamples - 1) - sk;
-                  e[k] = (sk >= 0 && sk < t.len) ? load_pcm(p.pcm, p.pcm_dtype, t.off + sk, p.pcm_scale) : 0.f;
-                }
-                v[u] = make_float4(e[0], e[1], e[2], e[3]);
+              for (int k = 0; k < 4; ++k) {
+                int sk = s + k;
+                if (sk < 0) sk = -sk;
+                if (sk >= kNSamples) sk = 2 * (kNSamples - 1) - sk;
+                e[k] = (sk >= 0 && sk < tm.len) ? load_pcm(p.pcm, p.pcm_dtype, tm.off + sk, p.pcm_scale) : 0.f;
               }
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < kBatch; ++u) {
-            const int g = g0 + 256 * u;
-            if (g < n_quads) {
-              float4 x = v[u];
-              if (p.norm != nullptr) {
-                const int s = s_begin + 4 * g;
-                float* e = reinterpret_cast<float*>(&x);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  int sk = s + k;
-                  if (sk < 0) sk = -sk;
-                  if (sk >= kNSamples) sk = 2 * (kNSamples - 1) - sk;
-                  if (sk >= 0 && sk < t.len) e[k] = (e[k] - mean) * rstd;
-                }
-              }
-              const int r = g / (kHop / 4);
-              *reinterpret_cast<float4*>(raw + r * kRawPitch + 4 * (g - r * (kHop / 4))) = x;
+              v[u] = make_float4(e[0], e[1], e[2], e[3]);
             }
           }
         }
-        // rows beyond the valid frames are read by the idle lanes' arithmetic: make them finite
-        for (int g = n_quads + wt; g < kRawRows * (kHop / 4); g += 256) {
-          const int r = g / (kHop / 4);
-          *reinterpret_cast<float4*>(raw + r * kRawPitch + 4 * (g - r * (kHop / 4))) = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          const int g = g0 + 256 * u;
+          if (g < n_quads) {
+            float4 x = v[u];
+            if (p.norm != nullptr) {
+              const int s = s_begin + 4 * g;
+              float* e = reinterpret_cast<float*>(&x);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                int sk = s + k;
+                if (sk < 0) sk = -sk;
+                if (sk >= kNSamples) sk = 2 * (kNSamples - 1) - sk;
+                if (sk >= 0 && sk < tm.len) e[k] = (e[k] - mean) * rstd;
+              }
+            }
+            const int r = g / (kHop / 4);
+            *reinterpret_cast<float4*>(raw + r * kRawPitch + 4 * (g - r * (kHop / 4))) = x;
+          }
         }
-        worker_bar();
       }
-      if (wt == 0) TCT(0, nt, 2);
-      // ---- tile maximum -> power-of-two scale ----
-      uint32_t mx = 0;
-#pragma unroll 4
-      for (int i = wt; i < kRawRows * (kHop / 4); i += 256) {
-        const int r = i / (kHop / 4), c = i - r * (kHop / 4);
-        float4 v = *reinterpret_cast<const float4*>(raw + r * kRawPitch + 4 * c);
-        if (r == kRawRows - 1 && 4 * c >= kRawLen - (kRawRows - 1) * kHop) v = make_float4(0.f, 0.f, 0.f, 0.f);  // beyond the tile
-        const float a = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
-        mx = max(mx, __float_as_uint(a));
+      // rows beyond the valid frames feed the idle lanes' arithmetic: make them finite
+      for (int g = n_quads + wt; g < kRawRows * (kHop / 4); g += 256) {
+        const int r = g / (kHop / 4);
+        *reinterpret_cast<float4*>(raw + r * kRawPitch + 4 * (g - r * (kHop / 4))) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      mx = __reduce_max_sync(0xffffffffu, mx);
+      worker_bar();
+      uint32_t mx = __reduce_max_sync(0xffffffffu, raw_absmax(raw, wt, 256));
       if (lane == 0) s_pmax[warp] = mx;
       worker_bar();
       mx = max(max(max(s_pmax[0], s_pmax[1]), max(s_pmax[2], s_pmax[3])), max(max(s_pmax[4], s_pmax[5]), max(s_pmax[6], s_pmax[7])));
-      // scale = 2^(14 - e) with e = unbiased exponent of the maximum (clamped so that the scale stays a normal float)
-      int e = (int)((mx >> 23) & 0xffu) - 127;
-      if (mx == 0u) e = 14;
-      e = max(-100, min(e, 100));
-      const float scale = __uint_as_float((uint32_t)(127 + 14 - e) << 23);
-      // y = (log10(mel_scaled * 2^(-2 (14 - e))) + 4) / 4 = lg2(mel_scaled) * C + (1 - 2 (14 - e) C)
-      const float tile_k = 1.0f - (float)(2 * (14 - e)) * (0.25f * kLog10_2);
-      // scaled window table (exact: the scale is a power of two), zero beyond the 400-point frame: with it the k-step
-      // loop below needs no per-k-step code (a fully unrolled version with FMUL immediates was instruction-cache bound)
-      if (wt < kKSteps * 16) {
-        float w4[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) w4[k] = (4 * wt + k < kNFft) ? __uint_as_float(kWinBits[4 * wt + k]) * scale : 0.f;
-        reinterpret_cast<float4*>(ws)[wt] = make_float4(w4[0], w4[1], w4[2], w4[3]);
-      }
-      worker_bar();  // ws complete; s_pmax may be rewritten by the next tile only after everybody has read it
-      if (wt == 0) TCT(0, nt, 3);
+      scale_from_max(mx, tm.scale, tm.tile_k);
+      write_ws(ws_sm + rb * kWsFloats, tm.scale, wt, 256);
+      worker_bar();  // ws complete; s_pmax free for the next staged tile
+    };
 
-      // ---- MMA phase: k-steps of 16 n2 (= 64 consecutive samples) for all four n1; the quarter's two warps take
-      //      alternate k-steps ----
-#pragma unroll 1
-      for (int j = (int)((ks & 1u) ^ (uint32_t)hh); j < kKSteps; j += 2) {
-        const uint32_t kj = ks + (uint32_t)j;  // running k-step index
-        uint32_t hv[4][8], lv[4][8];           // per n1: 16 fp16 hi (K order), 16 fp16 lo
+    // one k-step (16 n2 = 64 consecutive samples, all four n1) of the tile in raw buffer rb: window, split into fp16
+    // hi / lo, and hand the four operand slots to the tensor core as they become free.  kj = running k-step index.
+    auto prep_kstep = [&](uint32_t rb, int j, uint32_t kj) {
+      const float* const xrow = reinterpret_cast<const float*>(smem + kSmemRaw + rb * kRawBufBytes) + m * kRawPitch;
+      const float* const ws = ws_sm + rb * kWsFloats;
+      uint32_t hv[4][8], lv[4][8];  // per n1: 16 fp16 hi (K order), 16 fp16 lo
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          // the 32 samples of a half k-step never straddle a hop row (160 = 5 x 32)
-          const int n0 = 64 * j + 32 * c;
-          const float* xp = xrow + n0 + (kRawPitch - kHop) * ((n0 >= kHop ? 1 : 0) + (n0 >= 2 * kHop ? 1 : 0));
-          const float* wp = ws + n0;
-          float h[4][8], l[4][8];
+      for (int c = 0; c < 2; ++c) {
+        // the 32 samples of a half k-step never straddle a hop row (160 = 5 x 32)
+        const int n0 = 64 * j + 32 * c;
+        const float* xp = xrow + n0 + (kRawPitch - kHop) * ((n0 >= kHop ? 1 : 0) + (n0 >= 2 * kHop ? 1 : 0));
+        const float* wp = ws + n0;
+        float h[4][8], l[4][8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 x = *reinterpret_cast<const float4*>(xp + 4 * q);
-            const float4 w = *reinterpret_cast<const float4*>(wp + 4 * q);
-            const float y[4] = {x.x * w.x, x.y * w.y, x.z * w.z, x.w * w.w};
+        for (int q = 0; q < 8; ++q) {
+          const float4 x = *reinterpret_cast<const float4*>(xp + 4 * q);
+          const float4 w = *reinterpret_cast<const float4*>(wp + 4 * q);
+          const float y[4] = {x.x * w.x, x.y * w.y, x.z * w.z, x.w * w.w};
 #pragma unroll
-            for (int n1 = 0; n1 < 4; ++n1) {
-              const float hb = __uint_as_float(__float_as_uint(y[n1]) & 0xFFFFE000u);  // 11 significant bits: exact in fp16
-              h[n1][q] = hb;
-              l[n1][q] = y[n1] - hb;
-            }
+          for (int n1 = 0; n1 < 4; ++n1) {
+            const float hb = __uint_as_float(__float_as_uint(y[n1]) & 0xFFFFE000u);  // 11 significant bits: exact in fp16
+            h[n1][q] = hb;
+            l[n1][q] = y[n1] - hb;
           }
-#pragma unroll
-          for (int n1 = 0; n1 < 4; ++n1)
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              hv[n1][4 * c + u] = pack_h2(h[n1][2 * u], h[n1][2 * u + 1]);
-              lv[n1][4 * c + u] = pack_h2(l[n1][2 * u], l[n1][2 * u + 1]);
-            }
         }
-        // ---- hand the four slots to the tensor core as they become free ----
 #pragma unroll
-        for (int n1 = 0; n1 < 4; ++n1) {
-          // The MMAs of k-step kj - 1 have read this slot.  Their commits go to the barrier set of THAT k-step's parity:
-          // a parity wait cannot tell phase i from phase i + 2, and with the quarter's two warps alternating k-steps a
-          // single set would let a warp run two phases ahead.  This way each warp consumes every phase of "its" set.
-          mbar_wait(&bar_a_empty[hh ^ 1][n1], hh ? ((kj >> 1) & 1u) : (((kj >> 1) & 1u) ^ 1u), err_flag);
+        for (int n1 = 0; n1 < 4; ++n1)
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            hv[n1][4 * c + u] = pack_h2(h[n1][2 * u], h[n1][2 * u + 1]);
+            lv[n1][4 * c + u] = pack_h2(l[n1][2 * u], l[n1][2 * u + 1]);
+          }
+      }
+      // The MMAs of k-step kj - 1 have read a slot when their commit arrives.  Commits go to the barrier set of THAT
+      // k-step's parity: a parity wait cannot tell phase i from phase i + 2, and with the quarter's two warps
+      // alternating k-steps a single set would let a warp run two phases ahead.  This way each warp consumes every
+      // phase of "its" set.
+      const uint32_t par = hh ? ((kj >> 1) & 1u) : (((kj >> 1) & 1u) ^ 1u);
+#if WFE_TC_DEPOSIT == 1
+      // slots in two groups of two: one tcgen05.wait::st per group instead of per slot
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+#pragma unroll
+        for (int n1 = 2 * g; n1 < 2 * g + 2; ++n1) {
+          mbar_wait(&bar_a_empty[hh ^ 1][n1], par, err_flag);
           tc_fence_after();
           const uint32_t r[16] = {hv[n1][0], hv[n1][1], hv[n1][2], hv[n1][3], hv[n1][4], hv[n1][5], hv[n1][6], hv[n1][7],
                                   lv[n1][0], lv[n1][1], lv[n1][2], lv[n1][3], lv[n1][4], lv[n1][5], lv[n1][6], lv[n1][7]};
           tmem_st16(a_slot0 + 16 * n1, r);
-          tmem_st_wait();
-          tc_fence_before();
-          mbar_arrive(&bar_a_full[n1]);
         }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&bar_a_full[2 * g]);
+        mbar_arrive(&bar_a_full[2 * g + 1]);
+      }
+#else
+#pragma unroll
+      for (int n1 = 0; n1 < 4; ++n1) {
+        mbar_wait(&bar_a_empty[hh ^ 1][n1], par, err_flag);
+        tc_fence_after();
+        const uint32_t r[16] = {hv[n1][0], hv[n1][1], hv[n1][2], hv[n1][3], hv[n1][4], hv[n1][5], hv[n1][6], hv[n1][7],
+                                lv[n1][0], lv[n1][1], lv[n1][2], lv[n1][3], lv[n1][4], lv[n1][5], lv[n1][6], lv[n1][7]};
+        tmem_st16(a_slot0 + 16 * n1, r);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&bar_a_full[n1]);
+      }
+#endif
+    };
+
+    // scale + scaled window of a TMA tile whose maximum the workers have accumulated in s_tilemax[rb] (all workers,
+    // after a worker_bar that ordered the atomics); resets the accumulator for the buffer's next tile
+    auto finish_scale = [&](uint32_t rb, TileMeta& tm) {
+      if (tm.mode == kModeAsync || tm.mode == kModeAsyncHead) {
+        scale_from_max(s_tilemax[rb], tm.scale, tm.tile_k);
+        write_ws(ws_sm + rb * kWsFloats, tm.scale, wt, 256);
+      }
+    };
+    constexpr int kScanU = (5180 + 255) / 256;  // float4 per worker thread for a whole tile: 21
+
+    uint32_t ks = 0;   // running k-step index of the current tile's first k-step
+    uint32_t nt = 0;   // running count of non-silent tiles
+    TileMeta cur, nxt;
+    fetch(0, cur);
+    if (cur.mode == kModeAsync || cur.mode == kModeAsyncHead) {  // first tile: nobody has scanned it yet
+      const float mxf = raw_absmax_slice(reinterpret_cast<const float*>(smem + kSmemRaw), wt, 256, 0, kScanU);
+      const uint32_t mx = __reduce_max_sync(0xffffffffu, __float_as_uint(mxf));
+      if (lane == 0) atomicMax(&s_tilemax[0], mx);
+    }
+    worker_bar();
+    finish_scale(0, cur);
+    worker_bar();
+    if (wt == 0) s_tilemax[0] = 0u;  // next accumulated during tile 1's MMA phase (for tile 2), after more barriers
+    while (cur.mode != kModeDone) {
+      const uint32_t rb = nt & 1u;
+      const int t0 = cur.tile * kTileM;
+      const float tile_k = cur.tile_k;
+      if (wt == 0) TCT(0, nt, 3);
+      // the next tile is already in the other raw buffer (its TMA was issued one epilogue ago)
+      fetch(nt + 1, nxt);
+      const bool scan_next = nxt.mode == kModeAsync || nxt.mode == kModeAsyncHead;
+      const float* const raw_next = reinterpret_cast<const float*>(smem + kSmemRaw + (rb ^ 1u) * kRawBufBytes);
+      // ---- MMA phase: the quarter's two warps take alternate k-steps (running index parity == hh) ----
+#pragma unroll 1
+      for (int j = (int)((ks & 1u) ^ (uint32_t)hh); j < kKSteps; j += 2) {
+        prep_kstep(rb, j, ks + (uint32_t)j);
         if (lane == 0 && qt == 0) TCT(0, nt, 4 + j);
       }
-      ks += kKSteps;
       mbar_arrive(&bar_raw_empty[rb]);  // this thread is done reading the raw tile
+      // ---- maximum of the NEXT tile, in the shadow of the tensor core's last k-steps (interleaving it with the k-step
+      //      loop slowed the loop down by as much as it saved) ----
+      if (scan_next) {
+        const float mx_next = raw_absmax_slice(raw_next, wt, 256, 0, kScanU);
+        const uint32_t mx = __reduce_max_sync(0xffffffffu, __float_as_uint(mx_next));
+        if (lane == 0) atomicMax(&s_tilemax[rb ^ 1u], mx);
+      }
+      worker_bar();  // every warp's share of the next tile's maximum is in
+      finish_scale(rb ^ 1u, nxt);
 
       // ---- epilogue phase ----
       const bool valid = t0 + m < kNFrames;
-      OutT* const obase = reinterpret_cast<OutT*>(p.out) + (size_t)t.b * kNMel * kNFrames + t0 + m;
-      if (hh == 0 && p.mask != nullptr && valid) p.mask[(size_t)t.b * kNFrames + t0 + m] = ((t0 + m) * kHop < t.len) ? 1 : 0;
+      OutT* const obase = reinterpret_cast<OutT*>(p.out) + (size_t)cur.b * kNMel * kNFrames + t0 + m;
+      if (hh == 0 && p.mask != nullptr && valid) p.mask[(size_t)cur.b * kNFrames + t0 + m] = ((t0 + m) * kHop < cur.len) ? 1 : 0;
       if (wt == 0) TCT(1, nt, 0);
       mbar_wait(&bar_d_full, nt & 1u, err_flag);
       tc_fence_after();
       if (wt == 0) TCT(1, nt, 1);
       uint32_t rmax = 0u, rmin = 0x7f800000u;
-      uint32_t q0[16], q1[16], q2[16], q3[16];
+      uint32_t qb0_[4][8], qb1_[4][8];  // two register buffers of TMEM columns: [n1][2 pairs x (re, re, im, im)]
       f2 P0, P1, P2, P3;
 
-#define TC_LOAD(g, col)                         \
-  tmem_ld16(tlane + 0 * kN + (col), q0);        \
-  tmem_ld16(tlane + 1 * kN + (col), q1);        \
-  tmem_ld16(tlane + 2 * kN + (col), q2);        \
-  tmem_ld16(tlane + 3 * kN + (col), q3);        \
-  tmem_ld_wait();
+#define TC_LOAD(buf, col)                                  \
+  tmem_ld8(tlane + 0 * kN + (col), qb##buf##_[0]);         \
+  tmem_ld8(tlane + 1 * kN + (col), qb##buf##_[1]);         \
+  tmem_ld8(tlane + 2 * kN + (col), qb##buf##_[2]);         \
+  tmem_ld8(tlane + 3 * kN + (col), qb##buf##_[3]);
+#define TC_LOAD_WAIT() tmem_ld_wait();
       // columns of pair i within the group: (re k2, re k2+1, im k2, im k2+1).  T_n1 = Y_n1 * (cos - i sin):
       //   re = yr c + yi s, im = yi c - yr s; then the 4-point DFT over n1 and the four powers
 #define TC_TWID(qq, i, pp, n1m1, outr, outi)                                                                \
@@ -658,14 +759,14 @@ __global__ void __launch_bounds__(kThreads, 1)
     outr = vfma(yr, mk2(w.x, w.y), vmul(yi, mk2(w.z, w.w)));                                                \
     outi = vfma(yi, mk2(w.x, w.y), -vmul(yr, mk2(w.z, w.w)));                                               \
   }
-#define TC_PAIR(i, pp)                                                                                     \
+#define TC_PAIR(buf, i, pp)                                                                                \
   {                                                                                                        \
-    const f2 y0r = mk2(__uint_as_float(q0[4 * (i)]), __uint_as_float(q0[4 * (i) + 1]));                     \
-    const f2 y0i = mk2(__uint_as_float(q0[4 * (i) + 2]), __uint_as_float(q0[4 * (i) + 3]));                 \
+    const f2 y0r = mk2(__uint_as_float(qb##buf##_[0][4 * (i)]), __uint_as_float(qb##buf##_[0][4 * (i) + 1]));     \
+    const f2 y0i = mk2(__uint_as_float(qb##buf##_[0][4 * (i) + 2]), __uint_as_float(qb##buf##_[0][4 * (i) + 3])); \
     f2 t1r, t1i, t2r, t2i, t3r, t3i;                                                                       \
-    TC_TWID(q1, i, pp, 0, t1r, t1i)                                                                        \
-    TC_TWID(q2, i, pp, 1, t2r, t2i)                                                                        \
-    TC_TWID(q3, i, pp, 2, t3r, t3i)                                                                        \
+    TC_TWID(qb##buf##_[1], i, pp, 0, t1r, t1i)                                                             \
+    TC_TWID(qb##buf##_[2], i, pp, 1, t2r, t2i)                                                             \
+    TC_TWID(qb##buf##_[3], i, pp, 2, t3r, t3i)                                                             \
     const f2 s02r = y0r + t2r, s02i = y0i + t2i, d02r = y0r - t2r, d02i = y0i - t2i;                       \
     const f2 s13r = t1r + t3r, s13i = t1i + t3i, d13r = t1r - t3r, d13i = t1i - t3i;                       \
     const f2 x0r = s02r + s13r, x0i = s02i + s13i, x2r = s02r - s13r, x2i = s02i - s13i;                   \
@@ -705,6 +806,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
 #undef WFE_TC_GEN_NMEL
 #undef TC_LOAD
+#undef TC_LOAD_WAIT
 #undef TC_TWID
 #undef TC_PAIR
 #undef TC_RELEASE
@@ -728,6 +830,10 @@ __global__ void __launch_bounds__(kThreads, 1)
         __threadfence_block();
         mbar_arrive(&bar_st_full[nt & 1u]);  // release: the tile's global stores (ordered by __syncwarp) and s_red
       }
+      worker_bar();  // the next tile's window table is complete (and everybody has read its maximum)
+      if (wt == 0) s_tilemax[rb ^ 1u] = 0u;  // next written two tiles from now, after another worker_bar
+      cur = nxt;
+      ks += kKSteps;
       ++nt;
     }
   } else if (warp == 8) {
@@ -770,25 +876,60 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else if (warp == 9) {
     // =========================================== LOADER ===========================================
+    // One TMA per tile into the free raw buffer, the reflect-pad patch of a clip's first tile, and the tile's geometry:
+    // handed to the workers through bar_meta_full.  (Scanning the tile for its maximum here too was tried: one warp
+    // needs 9 k cycles for it and slows the two workers of its sub-partition -- the workers do it in their idle slots.)
     uint32_t nt = 0;
-    for (uint32_t id = blockIdx.x; id < p.total_tiles; id += gridDim.x) {
-      const Tile t = tile_info(p, id);
-      if (t.mode == kModeSilent) continue;
+    for (uint32_t id = blockIdx.x;; id += gridDim.x) {
+      Tile t;
+      t.mode = kModeDone;
+      t.b = t.tile = t.len = 0;
+      t.off = 0;
+      if (id < p.total_tiles) {
+        t = tile_info(p, id);
+        if (t.mode == kModeSilent) continue;
+      }
       const uint32_t rb = nt & 1u;
+      float* const raw = reinterpret_cast<float*>(smem + kSmemRaw + rb * kRawBufBytes);
       if (lane == 0) TCT(3, nt, 0);
-      mbar_wait(&bar_raw_empty[rb], ((nt >> 1) & 1u) ^ 1u, err_flag);  // prep has finished with this buffer's previous tile
+      mbar_wait(&bar_raw_empty[rb], ((nt >> 1) & 1u) ^ 1u, err_flag);  // the workers have finished with this buffer's previous tile
       if (lane == 0) TCT(3, nt, 1);
-      if (elect_one()) {
-        if (t.mode == kModeAsync || t.mode == kModeAsyncHead) {
+      float scale = 1.f, tile_k = 1.f;
+      if (t.mode == kModeAsync || t.mode == kModeAsyncHead) {
+        if (elect_one()) {
           mbar_arrive_expect_tx(&bar_raw_full[rb], kRawBoxBytes);
-          tma_load_2d(smem + kSmemRaw + rb * kRawBufBytes, &tmap,
-                      (int32_t)(t.off + (int64_t)(t.tile * kTileM * kHop - kNFft / 2)), 0, &bar_raw_full[rb]);
-        } else {
-          mbar_arrive(&bar_raw_full[rb]);  // generic staging: the prep warps fill the buffer themselves
+          tma_load_2d(raw, &tmap, (int32_t)(t.off + (int64_t)(t.tile * kTileM * kHop - kNFft / 2)), 0, &bar_raw_full[rb]);
+        }
+        __syncwarp();
+        mbar_wait(&bar_raw_full[rb], (nt >> 1) & 1u, err_flag);
+        if (lane == 0) TCT(3, nt, 2);
+        if (t.mode == kModeAsyncHead) {
+          // first tile of a clip: the TMA started 200 samples before the clip; replace them by the centred reflect pad
+          for (int i = lane; i < kNFft / 2; i += 32) {
+            const int s = kNFft / 2 - i;  // raw[i] = x[200 - i]
+            raw[i + (i >= kHop ? kRawPitch - kHop : 0)] = s < t.len ? load_pcm(p.pcm, p.pcm_dtype, t.off + s, p.pcm_scale) : 0.f;
+          }
+          __syncwarp();
         }
       }
+      if (lane == 0) {
+        TileMeta tm;
+        tm.b = t.b;
+        tm.tile = t.tile;
+        tm.len = t.len;
+        tm.mode = t.mode;
+        tm.off = t.off;
+        tm.scale = scale;
+        tm.tile_k = tile_k;
+        s_meta[rb] = tm;
+      }
       __syncwarp();
-      if (lane == 0) TCT(3, nt, 2);
+      if (lane == 0) {
+        __threadfence_block();
+        mbar_arrive(&bar_meta_full[rb]);
+        TCT(3, nt, 3);
+      }
+      if (t.mode == kModeDone) break;
       ++nt;
     }
   } else {

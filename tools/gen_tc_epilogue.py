@@ -92,17 +92,26 @@ def emit(n_mel: int, w: np.ndarray, out: list) -> None:
             for m in empty:
                 out.append(f"TC_FIN_ZERO({m})")
         pairs = sorted({p for (p, _, _, _) in seq})
+        # TMEM reads: groups of two pairs (8 columns per n1), double-buffered: the loads of group g + 1 are issued before
+        # the arithmetic of group g, the single tcgen05.wait::ld that follows the arithmetic then finds them done
+        n_groups = (len(pairs) + 1) // 2
+        out.append(f"TC_LOAD(0, {4 * pairs[0]})")
+        out.append("TC_LOAD_WAIT()")
         cur_pair, t = -1, 0
         pending_put = [m for m in shared] if hh == 1 else []
         for (p, e, f, b) in seq:
             if p != cur_pair:
                 i = pairs.index(p)
-                if i % 4 == 0:
-                    out.append(f"TC_LOAD({i // 4}, {4 * p})")  # group index, first TMEM column of the group
-                out.append(f"TC_PAIR({i % 4}, {p})")
+                if i % 2 == 0:
+                    g = i // 2
+                    if i > 0:
+                        out.append("TC_LOAD_WAIT()")
+                    if g + 1 < n_groups:
+                        out.append(f"TC_LOAD({(g + 1) % 2}, {4 * pairs[2 * (g + 1)]})")
+                    else:
+                        out.append("TC_RELEASE()  // this thread's last TMEM read is done")
+                out.append(f"TC_PAIR({(i // 2) % 2}, {i % 2}, {p})")
                 cur_pair = p
-                if p == pairs[-1]:
-                    out.append("TC_RELEASE()  // this thread's last TMEM read is done")
             comp = "x" if e == 0 else "y"
             for m in nz[b]:
                 wb = bits(w[b, m])
@@ -147,7 +156,7 @@ def emit_window(out: list) -> None:
     n = np.arange(400, dtype=np.float64)
     w = (0.5 - 0.5 * np.cos(2.0 * np.pi * n / 400.0)).astype(np.float32)
     out.append("#if defined(WFE_TC_GEN_WINDOW)")
-    out.append("__device__ constexpr uint32_t kWinBits[400] = {")
+    out.append("__device__ constexpr __align__(16) uint32_t kWinBits[400] = {")
     for i in range(0, 400, 8):
         out.append("  " + " ".join(f"0x{bits(x):08x}u," for x in w[i:i + 8]))
     out.append("};")
