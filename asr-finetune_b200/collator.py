@@ -15,7 +15,8 @@ from __future__ import annotations
 
 import ctypes as C
 import itertools
-from concurrent.futures import ThreadPoolExecutor
+import queue
+import threading
 from dataclasses import dataclass, field
 from typing import Any, Callable, Iterable, Optional, Sequence
 
@@ -67,9 +68,21 @@ def _pack_ids(label_lists: Sequence[Sequence[int]]):
     return buf, lens
 
 
+def _all_rows_start_with(label_lists, token_id: int) -> bool:
+    """The BOS-strip decision of the padding collator (ref ...datasets_and_collators.py:456-457), taken on the host:
+    the ids are host lists, so there is no reason to synchronise with the device for it."""
+    if len(label_lists) == 0:
+        return False
+    for ids in label_lists:
+        if len(ids) == 0 or int(ids[0]) != token_id:
+            return False
+    return True
+
+
 def collate_labels_and_features(fe: WhisperFeatureExtractor, label_lists, features, *, width: Optional[int],
-                                decoder_start_token_id: int, strip_bos: bool, device: Optional[torch.device] = None):
-    """-> (input_features (B, ...) fp32 CUDA or None, labels int64 CUDA).  One `wfe_collate` launch."""
+                                decoder_start_token_id: int, strip_bos: bool, device: Optional[torch.device] = None,
+                                feature_dtype: Optional[torch.dtype] = None):
+    """-> (input_features (B, ...) CUDA or None, labels int64 CUDA).  One `wfe_collate` launch, no host sync."""
     dev = device or fe.cuda_device()
     h = fe._handle(None, dev)
     B = len(label_lists)
@@ -82,7 +95,6 @@ def collate_labels_and_features(fe: WhisperFeatureExtractor, label_lists, featur
         d_packed = packed.to(dev, non_blocking=True)
         d_offs, d_ids = d_packed[:B + 1], d_packed[B + 1:]
         labels = torch.empty((B, width), dtype=torch.int64, device=dev)
-        flag = torch.zeros(1, dtype=torch.int32, device=dev)
         feat_out, srcs_ptr, feat_elems, keep = None, None, 0, []
         if features is not None:
             mats = []
@@ -112,11 +124,13 @@ def collate_labels_and_features(fe: WhisperFeatureExtractor, label_lists, featur
                     feat_out[i].copy_(m, non_blocking=True)
         _lib.check(h.lib.wfe_collate(h.ptr, d_ids.data_ptr() if d_ids.numel() else None, d_offs.data_ptr(), B, width,
                                      int(decoder_start_token_id), IGNORE_INDEX, labels.data_ptr() if width else None,
-                                     flag.data_ptr(), srcs_ptr, feat_elems,
+                                     None, srcs_ptr, feat_elems,
                                      feat_out.data_ptr() if srcs_ptr is not None else None, _cur_stream_ptr(dev)),
                    "wfe_collate")
-        if strip_bos and width > 0 and bool(flag.item()):  # ref ...:456-457
+        if strip_bos and width > 0 and _all_rows_start_with(label_lists, int(decoder_start_token_id)):  # ref ...:456-457
             labels = labels[:, 1:]
+        if feat_out is not None and feature_dtype is not None and feat_out.dtype != feature_dtype:
+            feat_out = feat_out.to(feature_dtype)
     del keep
     return feat_out, labels
 
@@ -148,41 +162,98 @@ class DataCollatorSpeechSeq2SeqWithPadding:
         return batch
 
 
+class _Worker:
+    """One long-lived helper thread (the label collate overlaps the audio pipeline in the host-tensor path); a
+    `ThreadPoolExecutor` built per call cost more than the work it ran at the reference's batch size of 8."""
+
+    def __init__(self):
+        self._q: "queue.Queue" = queue.Queue()
+        self._t = threading.Thread(target=self._run, name="wfe-collate", daemon=True)
+        self._t.start()
+
+    def _run(self):
+        while True:
+            fn, box, done = self._q.get()
+            try:
+                box.append((True, fn()))
+            except BaseException as e:  # handed back to the caller
+                box.append((False, e))
+            done.set()
+
+    def submit(self, fn):
+        box, done = [], threading.Event()
+        self._q.put((fn, box, done))
+
+        def result():
+            done.wait()
+            ok, val = box[0]
+            if not ok:
+                raise val
+            return val
+
+        return result
+
+
 class StreamingFrontendCollator:
     """Raw audio + transcriptions -> {"input_features", "labels"} entirely on the GPU.
 
     GPU form of `SimpleStreamingCollator.__call__`/_prepare_dataset (ref ...:133-256) with the HDF5 fetch
-    factored out: `batch` carries the decoded clips.  Keys: "audio" (list of 1-D float32/int16 arrays) and either
+    factored out: `batch` carries the decoded clips.  Keys: "audio" (list of 1-D float32/int16/float16 arrays) and either
     "labels" (list of id lists) or "transcription" (list of str, tokenised by `tokenizer`).  No BOS strip (ref quirk).
+
+    Samples whose fetch failed are DROPPED like the reference does (`(idx, None, None)` entries are filtered out,
+    ref ...:86-97,184): an entry whose audio is None (or empty) or whose label / transcription is None is skipped;
+    a batch with nothing left raises `RuntimeError("No valid data in batch")` (ref ...:186-187).
+
+    feature_dtype: torch.float32 (default) or float16 / bfloat16 — features rounded once in the kernel's epilogue, for
+    the autocast consumer (`fp16 = True`, ref:finetune/training/configs/largev3_debug.config:8).
     """
 
-    def __init__(self, feature_extractor, tokenizer: Optional[Callable] = None, device: Optional[str] = None):
+    def __init__(self, feature_extractor, tokenizer: Optional[Callable] = None, device: Optional[str] = None,
+                 feature_dtype: Optional[torch.dtype] = None):
         self.feature_extractor = _as_extractor(feature_extractor)
         self.tokenizer = tokenizer
         self.device = device
+        self.feature_dtype = feature_dtype
+        self.dropped = 0  # samples skipped so far
+        self._worker: Optional[_Worker] = None
 
     def __call__(self, batch) -> dict:
         audio = list(batch["audio"])
+        texts = batch["labels"] if "labels" in batch else batch.get("transcription")
+        if texts is None:
+            raise ValueError("need `labels` or `transcription`")
+        texts = list(texts)
+        if len(texts) != len(audio):
+            raise ValueError("audio and labels must have the same length")
+        keep = [i for i, (a, t) in enumerate(zip(audio, texts)) if a is not None and t is not None and len(a) > 0]
+        if len(keep) != len(audio):
+            self.dropped += len(audio) - len(keep)
+            audio = [audio[i] for i in keep]
+            texts = [texts[i] for i in keep]
         if len(audio) == 0:
             raise RuntimeError("No valid data in batch")  # ref ...:186-187
         if "labels" in batch:
-            label_lists = [x if isinstance(x, list) else list(x) for x in batch["labels"]]
+            label_lists = [x if isinstance(x, list) else list(x) for x in texts]
         else:
             if self.tokenizer is None:
                 raise ValueError("need `labels` or a tokenizer for `transcription`")
-            label_lists = [self.tokenizer(t if isinstance(t, str) else str(t)).input_ids for t in batch["transcription"]]
+            label_lists = [self.tokenizer(t if isinstance(t, str) else str(t)).input_ids for t in texts]
         fe = self.feature_extractor
         if self.device is not None and str(self.device) == "cpu":
             # host tensors wanted: the audio goes through the pipelined host entry (chunked H2D / kernels / D2H on three
-            # streams, GIL released) while a worker thread packs and collates the labels
+            # streams, GIL released) while the helper thread packs and collates the labels
             dev = fe.cuda_device()
-            with ThreadPoolExecutor(max_workers=1) as pool:
-                fut = pool.submit(lambda: collate_labels_and_features(fe, label_lists, None, width=None,
-                                                                      decoder_start_token_id=-1, strip_bos=False,
-                                                                      device=dev)[1].cpu())
-                feats = fe(audio, sampling_rate=fe.sampling_rate, return_tensors="pt")["input_features"]
-                return {"input_features": feats, "labels": fut.result()}
-        out = fe(audio, sampling_rate=fe.sampling_rate, return_tensors="pt", output_device="cuda")
+            if self._worker is None:
+                self._worker = _Worker()
+            fut = self._worker.submit(lambda: collate_labels_and_features(fe, label_lists, None, width=None,
+                                                                          decoder_start_token_id=-1, strip_bos=False,
+                                                                          device=dev)[1].cpu())
+            feats = fe(audio, sampling_rate=fe.sampling_rate, return_tensors="pt",
+                       output_dtype=self.feature_dtype)["input_features"]
+            return {"input_features": feats, "labels": fut()}
+        out = fe(audio, sampling_rate=fe.sampling_rate, return_tensors="pt", output_device="cuda",
+                 output_dtype=self.feature_dtype)
         _, labels = collate_labels_and_features(fe, label_lists, None, width=None, decoder_start_token_id=-1,
                                                 strip_bos=False, device=out["input_features"].device)
         return {"input_features": out["input_features"], "labels": labels}

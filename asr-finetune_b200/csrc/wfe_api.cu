@@ -462,7 +462,8 @@ int wfe_create(const wfe_config* cfg, const float* mel_filters, wfe_handle** out
   if (cfg->n_fft != wfe::kNFft || cfg->hop_length != wfe::kHop)
     return fail(WFE_ERR_UNSUPPORTED, "kernels are specialised for n_fft=400, hop_length=160 (every Whisper checkpoint)");
   if (cfg->n_mel < 1 || cfg->n_mel > 256) return fail(WFE_ERR_UNSUPPORTED, "n_mel must be in 1..256");
-  if (cfg->n_samples < wfe::kNFft) return fail(WFE_ERR_UNSUPPORTED, "n_samples must be >= 400 (n_fft)");
+  if (cfg->n_samples <= wfe::kNFft / 2)
+    return fail(WFE_ERR_UNSUPPORTED, "n_samples must exceed n_fft / 2 = 200 (centred reflect pad)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     cudaGetLastError();

@@ -116,6 +116,21 @@ class _Handle:
             pass
 
 
+_OUT_DTYPES = {torch.float32: _lib.WFE_OUT_F32, torch.float16: _lib.WFE_OUT_F16, torch.bfloat16: _lib.WFE_OUT_BF16}
+
+
+def _out_dtype(dtype) -> torch.dtype:
+    """`output_dtype` argument -> torch dtype (None = float32, what the reference extractor returns)."""
+    if dtype is None:
+        return torch.float32
+    if isinstance(dtype, str):
+        dtype = {"float32": torch.float32, "fp32": torch.float32, "float16": torch.float16, "fp16": torch.float16,
+                 "half": torch.float16, "bfloat16": torch.bfloat16, "bf16": torch.bfloat16}.get(dtype.lower(), dtype)
+    if dtype not in _OUT_DTYPES:
+        raise TypeError(f"output_dtype must be float32, float16 or bfloat16, got {dtype!r}")
+    return dtype
+
+
 def _cur_stream_ptr(device: torch.device) -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
@@ -225,25 +240,33 @@ class WhisperFeatureExtractor:
     # ---- the hot path -----------------------------------------------------------------------------------
     def logmel_device(self, pcm: torch.Tensor, offsets: torch.Tensor, batch: int, *, n_samples: Optional[int] = None,
                       pcm_scale: float = 1.0, do_normalize: bool = False, return_attention_mask: bool = False,
-                      out: Optional[torch.Tensor] = None, lengths: Optional[torch.Tensor] = None):
-        """Device-resident entry: ragged `pcm` (float32 or int16 CUDA tensor) + int64 `offsets` (CUDA; B+1 entries, or B
-        clip starts when `lengths` (B, int64, CUDA) is given — starts on 16-byte boundaries take the 128-bit load path)
-        -> (input_features (B, n_mel, n_frames) fp32 CUDA, attention_mask (B, n_frames) int32 CUDA or None).
-        Runs on the current torch stream; no host synchronisation."""
+                      out: Optional[torch.Tensor] = None, lengths: Optional[torch.Tensor] = None, out_dtype=None):
+        """Device-resident entry: ragged `pcm` (float32, int16 or float16 CUDA tensor) + int64 `offsets` (CUDA; B+1
+        entries, or B clip starts when `lengths` (B, int64, CUDA) is given — starts on 16-byte boundaries take the TMA /
+        128-bit load paths) -> (input_features (B, n_mel, n_frames) CUDA, attention_mask (B, n_frames) int32 CUDA or
+        None).  `out_dtype`: float32 (default, the reference's), float16 or bfloat16 — the fp32 result rounded once in
+        the kernel's epilogue (the cast an autocast consumer applies anyway).  Runs on the current torch stream; no host
+        synchronisation."""
         dev = pcm.device
         h = self._handle(n_samples, dev)
         if pcm.dtype == torch.float32:
             dt = _lib.WFE_PCM_F32
         elif pcm.dtype == torch.int16:
             dt = _lib.WFE_PCM_I16
+        elif pcm.dtype == torch.float16:
+            dt = _lib.WFE_PCM_F16
         else:
-            raise TypeError(f"pcm must be float32 or int16, got {pcm.dtype}")
+            raise TypeError(f"pcm must be float32, int16 or float16, got {pcm.dtype}")
         assert offsets.dtype == torch.int64 and offsets.is_cuda
         assert offsets.numel() == (batch + 1 if lengths is None else batch)
         assert lengths is None or (lengths.dtype == torch.int64 and lengths.is_cuda and lengths.numel() == batch)
         len_ptr = lengths.data_ptr() if lengths is not None else None
         if out is None:
-            out = torch.empty((batch, h.n_mel, h.n_frames), dtype=torch.float32, device=dev)
+            out = torch.empty((batch, h.n_mel, h.n_frames), dtype=_out_dtype(out_dtype), device=dev)
+        elif out_dtype is not None and out.dtype != _out_dtype(out_dtype):
+            raise TypeError("`out` does not have the requested out_dtype")
+        if out.dtype not in _OUT_DTYPES or not out.is_contiguous():
+            raise TypeError("`out` must be a contiguous float32 / float16 / bfloat16 tensor")
         mask = torch.empty((batch, h.n_frames), dtype=torch.int32, device=dev) if return_attention_mask else None
         scratch = torch.empty(max(h.scratch_bytes(batch), 4), dtype=torch.uint8, device=dev)
         stream = _cur_stream_ptr(dev)
@@ -253,9 +276,9 @@ class WhisperFeatureExtractor:
             _lib.check(h.lib.wfe_clip_stats(h.ptr, pcm.data_ptr(), dt, pcm_scale, offsets.data_ptr(), len_ptr, batch,
                                             stats.data_ptr(), stream), "wfe_clip_stats")
             stats_ptr = stats.data_ptr()
-        _lib.check(h.lib.wfe_logmel(h.ptr, pcm.data_ptr(), dt, pcm_scale, offsets.data_ptr(), len_ptr, batch, stats_ptr,
-                                    out.data_ptr(), mask.data_ptr() if mask is not None else None,
-                                    scratch.data_ptr(), stream), "wfe_logmel")
+        _lib.check(h.lib.wfe_logmel_ex(h.ptr, pcm.data_ptr(), dt, pcm_scale, offsets.data_ptr(), len_ptr, batch, stats_ptr,
+                                       out.data_ptr(), _OUT_DTYPES[out.dtype], mask.data_ptr() if mask is not None else None,
+                                       scratch.data_ptr(), stream), "wfe_logmel")
         self._last_scratch = (h, scratch, batch)
         return out, mask
 
@@ -264,20 +287,36 @@ class WhisperFeatureExtractor:
         h, scratch, batch = self._last_scratch
         return int(h.lib.wfe_debug_scratch_error(h.ptr, scratch.data_ptr(), batch))
 
-    def _extract_host(self, clips: Sequence[np.ndarray], n_samples: int, do_normalize: bool, want_mask: bool):
-        """Host numpy clips -> host (pinned) torch tensors through the pipelined C entry point."""
+    def uses_tensor_cores(self, n_samples: Optional[int] = None) -> bool:
+        """True when this configuration runs on the tcgen05 kernel (480000-sample window, slaney 80 / 128 mel bank)."""
+        h = self._handle(n_samples)
+        return bool(h.lib.wfe_uses_tensor_cores(h.ptr))
+
+    def _extract_host(self, clips: Sequence[np.ndarray], n_samples: int, do_normalize: bool, want_mask: bool,
+                      out_dtype=None):
+        """Host numpy clips -> host (pinned) torch tensors through the pipelined C entry point.  The PCM crosses PCIe in
+        its own width only when EVERY clip has that 2-byte dtype (int16 as-is, like HF; float16 widened exactly);
+        mixed batches have already been converted to float32 by `__call__`."""
         dev = self.cuda_device()
         h = self._handle(n_samples, dev)
         B = len(clips)
-        dt = _lib.WFE_PCM_I16 if clips[0].dtype == np.int16 else _lib.WFE_PCM_F32
+        kinds = {c.dtype for c in clips}
+        if kinds == {np.dtype(np.int16)}:
+            dt = _lib.WFE_PCM_I16
+        elif kinds == {np.dtype(np.float16)}:
+            dt = _lib.WFE_PCM_F16
+        else:
+            assert kinds == {np.dtype(np.float32)}, kinds
+            dt = _lib.WFE_PCM_F32
         ptrs = (C.c_void_p * B)(*[c.ctypes.data for c in clips])
         lens = (C.c_int64 * B)(*[int(c.shape[0]) for c in clips])
-        out = torch.empty((B, h.n_mel, h.n_frames), dtype=torch.float32, pin_memory=True)
+        odt = _out_dtype(out_dtype)
+        out = torch.empty((B, h.n_mel, h.n_frames), dtype=odt, pin_memory=True)
         mask = torch.empty((B, h.n_frames), dtype=torch.int32, pin_memory=True) if want_mask else None
         up, down = C.c_uint64(0), C.c_uint64(0)
-        _lib.check(h.lib.wfe_extract_host(h.ptr, ptrs, lens, B, dt, 1.0, int(bool(do_normalize)), out.data_ptr(),
-                                          mask.data_ptr() if mask is not None else None, C.byref(up), C.byref(down)),
-                   "wfe_extract_host")
+        _lib.check(h.lib.wfe_extract_host_ex(h.ptr, ptrs, lens, B, dt, 1.0, int(bool(do_normalize)), out.data_ptr(),
+                                             _OUT_DTYPES[odt], mask.data_ptr() if mask is not None else None,
+                                             C.byref(up), C.byref(down)), "wfe_extract_host")
         self.last_transfer_bytes = (int(up.value), int(down.value))
         return out, mask
 
@@ -292,6 +331,7 @@ class WhisperFeatureExtractor:
         `output_device="cuda"` (extension) to keep the returned tensors on the GPU (`return_tensors="pt"` implied).
         """
         output_device = kwargs.pop("output_device", None)
+        output_dtype = kwargs.pop("output_dtype", None)  # extension: float16 / bfloat16 features (fused cast)
         if sampling_rate is not None:
             if sampling_rate != self.sampling_rate:
                 raise ValueError(
@@ -305,7 +345,8 @@ class WhisperFeatureExtractor:
         if self.dither != 0.0:
             # HF adds `dither * randn` to the PADDED waveform (HF ...:146-147): the padded batch is built on the device
             return self._call_dithered(raw_speech, truncation, pad_to_multiple_of, return_tensors,
-                                       return_attention_mask, padding, max_length, do_normalize, output_device)
+                                       return_attention_mask, padding, max_length, do_normalize, output_device,
+                                       output_dtype)
 
         # ---- batched / unbatched normalisation (HF ...:274-290) ----
         if torch.is_tensor(raw_speech):
@@ -313,7 +354,8 @@ class WhisperFeatureExtractor:
                 raise ValueError(f"Only mono-channel audio is supported for input to {self}")
             clips_t = [raw_speech] if raw_speech.dim() == 1 else list(raw_speech)
             return self._call_device_tensors(clips_t, truncation, pad_to_multiple_of, return_tensors,
-                                             return_attention_mask, padding, max_length, do_normalize, output_device)
+                                             return_attention_mask, padding, max_length, do_normalize, output_device,
+                                             output_dtype)
         is_batched_numpy = isinstance(raw_speech, np.ndarray) and raw_speech.ndim > 1
         if is_batched_numpy and raw_speech.ndim > 2:
             raise ValueError(f"Only mono-channel audio is supported for input to {self}")
@@ -321,16 +363,15 @@ class WhisperFeatureExtractor:
                                           isinstance(raw_speech[0], (np.ndarray, tuple, list, torch.Tensor)))
         if is_batched and len(raw_speech) > 0 and torch.is_tensor(raw_speech[0]):
             return self._call_device_tensors(list(raw_speech), truncation, pad_to_multiple_of, return_tensors,
-                                             return_attention_mask, padding, max_length, do_normalize, output_device)
+                                             return_attention_mask, padding, max_length, do_normalize, output_device,
+                                             output_dtype)
         seqs = list(raw_speech) if is_batched else [raw_speech]
-        clips = []
-        for s in seqs:
-            a = np.asarray(s)
-            if a.dtype != np.int16:
-                a = a if a.dtype == np.float32 else a.astype(np.float32)  # fp64 / lists -> fp32 (HF ...:282-286)
-            if a.ndim != 1:
-                a = a.reshape(-1)
-            clips.append(np.ascontiguousarray(a))
+        clips = [np.asarray(s) for s in seqs]
+        # int16 / float16 PCM travels in its own width only when the WHOLE batch has that dtype (the kernels convert on
+        # load); anything else becomes float32 like HF does (fp64 / lists -> fp32, HF ...:282-286)
+        narrow = len({c.dtype for c in clips}) == 1 and clips[0].dtype in (np.int16, np.float16)
+        clips = [np.ascontiguousarray((c if narrow or c.dtype == np.float32 else c.astype(np.float32)).reshape(-1))
+                 for c in clips]
 
         n_samples, lengths = self._resolve_length([int(c.shape[0]) for c in clips], truncation, padding, max_length,
                                                   pad_to_multiple_of)
@@ -339,46 +380,62 @@ class WhisperFeatureExtractor:
         if output_device is not None and str(output_device).startswith("cuda"):
             return self._call_device_tensors([torch.from_numpy(c) for c in clips], truncation, pad_to_multiple_of,
                                              return_tensors, return_attention_mask, padding, max_length, do_normalize,
-                                             output_device)
-        feats, mask = self._extract_host(clips, n_samples, norm, want_mask)
-        data = {"input_features": feats if return_tensors in ("pt", "torch") else feats.numpy()}
+                                             output_device, output_dtype)
+        clips = [c[:n] for c, n in zip(clips, lengths)]  # truncation (a no-op for clips that fit)
+        feats, mask = self._extract_host(clips, n_samples, norm, want_mask, output_dtype)
+        if return_tensors in ("pt", "torch"):
+            data = {"input_features": feats}
+        else:  # numpy has no bfloat16: hand such features out as torch tensors whatever `return_tensors` says
+            data = {"input_features": feats.numpy() if feats.dtype != torch.bfloat16 else feats}
         if want_mask:
             data["attention_mask"] = mask if return_tensors in ("pt", "torch") else mask.numpy()
         return BatchFeature(data)
 
     # ---- helpers ----------------------------------------------------------------------------------------
     def _resolve_length(self, lens, truncation, padding, max_length, pad_to_multiple_of):
-        """Padded/truncated sample count the STFT runs on (HF:feature_extraction_sequence_utils.py:51-334)."""
+        """-> (n, per-clip lengths): the common sample count `n` the STFT runs on and how many samples of each clip are
+        used.  Follows `SequenceFeatureExtractor.pad` (HF:feature_extraction_sequence_utils.py:51-334): truncate to
+        `max_length` (rounded up to `pad_to_multiple_of`) if `truncation`; pad to the longest / to `max_length` (rounded
+        up) unless `padding` is False / "do_not_pad"; clips already longer than the target are left alone.  HF then
+        stacks the clips into one array — clips of different final lengths fail there with the numpy error reproduced
+        below.  Any common length >= 201 works (frames = n // 160; HF drops the last of the n // 160 + 1 STFT frames)."""
         max_length = max_length if max_length else self.n_samples
-        if padding in (True, "longest"):
-            target = max(min(n, max_length) if truncation else n for n in lens)
-        elif padding in ("max_length", None) or padding is False or padding == "do_not_pad":
-            if padding is False or padding == "do_not_pad":
-                raise NotImplementedError("padding='do_not_pad' yields ragged features; not supported by the GPU frontend")
-            target = max_length
+        if padding is True or padding == "longest":
+            strategy = "longest"
+        elif padding == "max_length" or padding is None:
+            strategy = "max_length"
+        elif padding is False or padding == "do_not_pad":
+            strategy = "do_not_pad"
         else:
             raise ValueError(f"unknown padding strategy {padding!r}")
-        if not truncation and max(lens) > target:
-            raise NotImplementedError("truncation=False with clips longer than max_length is not supported")
-        if pad_to_multiple_of is not None and target % pad_to_multiple_of != 0:
-            target = ((target // pad_to_multiple_of) + 1) * pad_to_multiple_of
-        if target % self.hop_length != 0 or target < self.n_fft:
-            raise NotImplementedError(f"padded length {target} must be a multiple of hop_length={self.hop_length} "
-                                      f"and >= n_fft for the sm_100a frontend")
-        return target, [min(n, target) for n in lens]
+        up = (lambda n: ((n // pad_to_multiple_of) + 1) * pad_to_multiple_of
+              if pad_to_multiple_of and n % pad_to_multiple_of else n)
+        cut = [min(n, up(max_length)) if truncation else n for n in lens]
+        if strategy == "do_not_pad":
+            final = cut
+        else:
+            target = up(max(cut) if strategy == "longest" else max_length)
+            final = [max(n, target) for n in cut]
+        if len(set(final)) != 1:
+            raise ValueError("axes don't match array")  # what numpy raises inside HF for a ragged batch
+        n = final[0]
+        if n <= self.n_fft // 2:
+            raise NotImplementedError(f"padded length {n} is too short for the centred reflect pad ({self.n_fft // 2})")
+        return n, cut
 
     def _call_device_tensors(self, clips, truncation, pad_to_multiple_of, return_tensors, return_attention_mask, padding,
-                             max_length, do_normalize, output_device):
+                             max_length, do_normalize, output_device, output_dtype=None):
         """Input given as torch tensors (CPU or CUDA): results stay on the GPU unless asked otherwise."""
         dev = self.cuda_device() if not clips[0].is_cuda else clips[0].device
         clips = [c.reshape(-1) for c in clips]
-        n_samples, _ = self._resolve_length([int(c.numel()) for c in clips], truncation, padding, max_length,
-                                            pad_to_multiple_of)
+        n_samples, lens_used = self._resolve_length([int(c.numel()) for c in clips], truncation, padding, max_length,
+                                                    pad_to_multiple_of)
         want_mask = bool(return_attention_mask if return_attention_mask is not None else self.return_attention_mask)
         norm = bool(do_normalize) if do_normalize is not None else bool(self.do_normalize)
-        dt = torch.int16 if clips[0].dtype == torch.int16 else torch.float32
+        kinds = {c.dtype for c in clips}
+        dt = clips[0].dtype if len(kinds) == 1 and clips[0].dtype in (torch.int16, torch.float16) else torch.float32
         B = len(clips)
-        lens = np.array([min(int(c.numel()), n_samples) for c in clips], dtype=np.int64)
+        lens = np.array(lens_used, dtype=np.int64)
         meta = np.zeros(2 * B, dtype=np.int64)  # clip starts (16-byte aligned), then lengths: one H2D copy
         meta[B:] = lens
         if B > 1:
@@ -387,22 +444,22 @@ class WhisperFeatureExtractor:
         with torch.cuda.device(dev):
             pcm = torch.empty(total + 8, dtype=dt, device=dev)
             for c, o, n in zip(clips, meta[:B].tolist(), lens.tolist()):
-                pcm[o:o + n].copy_(c[:n].to(dt), non_blocking=True)
+                pcm[o:o + n].copy_(c[:n], non_blocking=True)  # copy_ converts a stray dtype to `dt`
             d_meta = torch.from_numpy(meta).to(dev, non_blocking=True)
             feats, mask = self.logmel_device(pcm, d_meta[:B], B, n_samples=n_samples, do_normalize=norm,
-                                             return_attention_mask=want_mask, lengths=d_meta[B:])
+                                             return_attention_mask=want_mask, lengths=d_meta[B:], out_dtype=output_dtype)
         keep = output_device is not None and str(output_device).startswith("cuda") or (output_device is None and clips[0].is_cuda)
         if not keep:
             feats = feats.cpu()
             mask = mask.cpu() if mask is not None else None
-        as_pt = keep or return_tensors in ("pt", "torch")
+        as_pt = keep or return_tensors in ("pt", "torch") or feats.dtype == torch.bfloat16
         data = {"input_features": feats if as_pt else feats.numpy()}
         if want_mask:
             data["attention_mask"] = mask if as_pt else mask.numpy()
         return BatchFeature(data)
 
     def _call_dithered(self, raw_speech, truncation, pad_to_multiple_of, return_tensors, return_attention_mask, padding,
-                       max_length, do_normalize, output_device):
+                       max_length, do_normalize, output_device, output_dtype=None):
         """`dither != 0`: zero-pad to the target length on the device, add `dither * N(0, 1)` to every sample of the
         padded buffer (padding included, as HF does), then run the kernels on the full-length clips.  The noise comes
         from torch's CUDA generator, so results are reproducible under `torch.manual_seed` but not bit-equal to HF."""
@@ -433,7 +490,7 @@ class WhisperFeatureExtractor:
                     pcm[i, :n] = (v - v.mean()) / torch.sqrt(v.var(unbiased=False) + 1e-7)
             pcm.add_(torch.randn(pcm.shape, dtype=pcm.dtype, device=dev), alpha=float(self.dither))
             offs = torch.arange(B + 1, dtype=torch.int64, device=dev) * n_samples
-            feats, _ = self.logmel_device(pcm.view(-1), offs, B, n_samples=n_samples)
+            feats, _ = self.logmel_device(pcm.view(-1), offs, B, n_samples=n_samples, out_dtype=output_dtype)
             mask = None
             if want_mask:
                 t = torch.arange(n_samples // self.hop_length, device=dev) * self.hop_length

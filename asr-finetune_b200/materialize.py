@@ -9,8 +9,11 @@ The reference can pre-compute `input_features` / `labels` once and train from th
   * training reads them back through `collate_parquet` (`.../datasets_and_collators.py:279-294`).
 
 Here the arrays come from the sm_100a kernels (`wfe_logmel`, `wfe_collate`); storage is plain pyarrow (no Ray): one row
-per sample, `input_features` / `labels` as fixed-size lists with their shapes in the schema metadata.  HDF5 decode and
-tokenisation stay outside (the callers pass decoded PCM and token ids), as everywhere in this package.
+per sample, `input_features` / `labels` as Arrow FIXED-SHAPE TENSOR columns (`arrow.fixed_shape_tensor`, the canonical
+extension type; Ray Data writes ndarray columns the same way, as tensors with a fixed shape), so that any Arrow reader
+gets (n_mel, 3000) float32 / (L,) int64 arrays per row -- which is what the reference's unmodified `collate_parquet`
+stacks (tests/test_materialize_cpu.py feeds it rows read back with plain pyarrow).  HDF5 decode and tokenisation stay
+outside (the callers pass decoded PCM and token ids), as everywhere in this package.
 """
 from __future__ import annotations
 
@@ -82,10 +85,10 @@ def write_parquet(path: str, batches: Iterable[dict], row_group_size: int = 64) 
             cur = (tuple(f.shape[1:]), tuple(lab.shape[1:]))
             if shapes is None:
                 shapes = cur
+                f_type = pa.fixed_shape_tensor(pa.float32(), list(cur[0]))
+                l_type = pa.fixed_shape_tensor(pa.int64(), list(cur[1]))
                 schema = pa.schema(
-                    [pa.field("idx", pa.int64()),
-                     pa.field("input_features", pa.list_(pa.float32(), int(np.prod(cur[0])))),
-                     pa.field("labels", pa.list_(pa.int64(), int(np.prod(cur[1]))))],
+                    [pa.field("idx", pa.int64()), pa.field("input_features", f_type), pa.field("labels", l_type)],
                     metadata={"input_features_shape": json.dumps(cur[0]), "labels_shape": json.dumps(cur[1]),
                               "producer": "asr_finetune_b200"})
                 writer = pq.ParquetWriter(path, schema)
@@ -93,9 +96,8 @@ def write_parquet(path: str, batches: Iterable[dict], row_group_size: int = 64) 
                 raise ValueError(f"batch shapes {cur} differ from the file's {shapes} (use a fixed label width)")
             n = f.shape[0]
             table = pa.Table.from_arrays(
-                [pa.array(ids),
-                 pa.FixedSizeListArray.from_arrays(pa.array(f.reshape(-1)), int(np.prod(cur[0]))),
-                 pa.FixedSizeListArray.from_arrays(pa.array(lab.reshape(-1)), int(np.prod(cur[1])))],
+                [pa.array(ids), pa.FixedShapeTensorArray.from_numpy_ndarray(f),
+                 pa.FixedShapeTensorArray.from_numpy_ndarray(lab)],
                 schema=schema)
             writer.write_table(table, row_group_size=row_group_size)
             rows += n
@@ -117,19 +119,21 @@ def iter_parquet(path: str, batch_size: int, columns: Sequence[str] = ("idx", "i
     meta = pf.schema_arrow.metadata or {}
     fshape = tuple(json.loads(meta.get(b"input_features_shape", b"[]")))
     lshape = tuple(json.loads(meta.get(b"labels_shape", b"[]")))
+    def rows(col, shape):
+        if hasattr(col, "to_numpy_ndarray"):  # fixed-shape tensor column
+            arr = col.to_numpy_ndarray()
+        else:  # files written by round 1: flat fixed-size lists + the shape in the schema metadata
+            arr = col.flatten().to_numpy(zero_copy_only=False).reshape((len(col),) + (shape if shape else (-1,)))
+        return [arr[i] for i in range(arr.shape[0])]
+
     for rb in pf.iter_batches(batch_size=batch_size, columns=list(columns)):
-        n = rb.num_rows
         out: dict = {}
         if "idx" in columns:
             out["idx"] = rb.column(rb.schema.get_field_index("idx")).to_numpy(zero_copy_only=False)
         if "input_features" in columns:
-            flat = rb.column(rb.schema.get_field_index("input_features")).flatten().to_numpy(zero_copy_only=False)
-            arr = flat.reshape((n,) + (fshape if fshape else (-1,)))
-            out["input_features"] = [arr[i] for i in range(n)]
+            out["input_features"] = rows(rb.column(rb.schema.get_field_index("input_features")), fshape)
         if "labels" in columns:
-            flat = rb.column(rb.schema.get_field_index("labels")).flatten().to_numpy(zero_copy_only=False)
-            arr = flat.reshape((n,) + (lshape if lshape else (-1,)))
-            out["labels"] = [arr[i] for i in range(n)]
+            out["labels"] = rows(rb.column(rb.schema.get_field_index("labels")), lshape)
         yield out
 
 

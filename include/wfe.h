@@ -77,7 +77,7 @@ typedef struct wfe_config {
   int32_t n_mel;         /* feature_size: 80 (whisper-small) or 128 (large-v3); any 1..256 */
   int32_t n_fft;         /* must be 400 */
   int32_t hop_length;    /* must be 160 */
-  int32_t n_samples;     /* chunk_length * sampling_rate = 480000; any value >= 400 (n_frames = n_samples / 160, rounded down) */
+  int32_t n_samples;     /* chunk_length * sampling_rate = 480000; any value > 200 (n_frames = n_samples / 160, rounded down) */
   int32_t sampling_rate; /* 16000 (informational; checked by the Python shim like HF does) */
   int32_t device;        /* CUDA device ordinal (LOCAL_RANK) */
 } wfe_config;

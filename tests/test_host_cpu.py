@@ -67,10 +67,45 @@ def test_resolve_length_rules():
     assert fe._resolve_length([3, 640000], True, "max_length", None, None) == (480000, [3, 480000])
     assert fe._resolve_length([16000, 32000], True, "longest", None, None) == (32000, [16000, 32000])
     assert fe._resolve_length([16000], True, "max_length", 160000, None) == (160000, [16000])
+    # the rules of HF's SequenceFeatureExtractor.pad (probed against the installed extractor, see the live test below)
+    assert fe._resolve_length([16001], True, "longest", None, None) == (16001, [16001])  # any length: frames = n // 160
+    assert fe._resolve_length([48077], True, "do_not_pad", None, None) == (48077, [48077])
+    assert fe._resolve_length([48077], False, "max_length", 32000, None) == (48077, [48077])  # longer than the target: kept
+    assert fe._resolve_length([48077], True, "max_length", 32077, None) == (32077, [32077])
+    assert fe._resolve_length([100, 300], True, "longest", None, 256) == (512, [100, 300])
+    with pytest.raises(ValueError, match="axes don't match array"):  # ragged batch: numpy's error inside HF
+        fe._resolve_length([48077, 20000], True, "do_not_pad", None, None)
+    with pytest.raises(ValueError, match="axes don't match array"):
+        fe._resolve_length([48077, 20000], False, "max_length", 30000, None)
     with pytest.raises(NotImplementedError):
-        fe._resolve_length([16001], True, "longest", None, None)  # not a multiple of hop
+        fe._resolve_length([150], True, "longest", None, None)  # shorter than the centred reflect pad
     with pytest.raises(ValueError):
         fe._resolve_length([16000], True, "bogus", None, None)
+
+
+def test_resolve_length_agrees_with_the_installed_extractor():
+    """Frame counts / errors of the drop-in's length rules vs transformers' own padding logic (CPU, live)."""
+    tr = pytest.importorskip("transformers")
+    hf = tr.WhisperFeatureExtractor(feature_size=80)
+    fe = pkg.WhisperFeatureExtractor(feature_size=80)
+    x = np.random.default_rng(0).standard_normal(48077).astype(np.float32)
+    cases = [([x], dict(padding="do_not_pad")), ([x], dict(padding=False)), ([x], dict(padding="longest")),
+             ([x], dict(truncation=False, max_length=32000)), ([x], dict(padding="max_length", max_length=32077)),
+             ([x, x[:20000]], dict(padding="longest")), ([x, x[:20000]], dict(padding="do_not_pad")),
+             ([x, x[:20000]], dict(truncation=False, max_length=30000)), ([x[:777]], dict(padding="longest", pad_to_multiple_of=256))]
+    for clips, kw in cases:
+        args = ([len(c) for c in clips], kw.get("truncation", True), kw.get("padding", "max_length"), kw.get("max_length"),
+                kw.get("pad_to_multiple_of"))
+        try:
+            ref = hf(clips if len(clips) > 1 else clips[0], sampling_rate=16000, return_attention_mask=True, **kw)
+        except ValueError as e:
+            with pytest.raises(ValueError, match=str(e)[:10]):
+                fe._resolve_length(*args)
+            continue
+        n, used = fe._resolve_length(*args)
+        assert ref["input_features"].shape[-1] == n // 160, (kw, n)
+        assert ref["attention_mask"].shape[-1] == n // 160
+        assert ref["attention_mask"].sum(-1).tolist() == [len(range(0, u, 160)) if u < n else n // 160 for u in used]
 
 
 def test_pad_is_a_bit_exact_stack_like_the_reference(collate_golden):

@@ -66,3 +66,34 @@ def test_to_host_batch_adds_idx_and_converts_tensors():
     out = pkg.to_host_batch({"input_features": torch.zeros(2, 80, 3000), "labels": torch.full((2, 7), -100)})
     assert out["input_features"].shape == (2, 80, 3000) and out["labels"].dtype == np.int64
     np.testing.assert_array_equal(out["idx"], [0, 1])
+
+
+def test_plain_pyarrow_rows_feed_the_unmodified_reference_collate_parquet(tmp_path):
+    """The on-disk format is readable without this package: rows read with plain pyarrow (Arrow fixed-shape tensors)
+    go straight into the reference's own `collate_parquet` (ref ...datasets_and_collators.py:279-294), imported
+    unmodified from /root/reference (build container only)."""
+    import sys
+
+    import pyarrow.parquet as pq
+    import torch
+
+    if not os.path.isdir("/root/reference/finetune/training"):
+        pytest.skip("reference tree not mounted (build container only)")
+    from conftest import GOLDEN_DIR
+
+    sys.path.insert(0, GOLDEN_DIR)
+    import make_golden as mg
+
+    ref = mg.import_reference_collators()
+    path = os.path.join(tmp_path, "train.parquet")
+    b = _batch(6, n_mel=128, seed=11)
+    pkg.write_parquet(path, [b])
+    table = pq.read_table(path)  # no asr_finetune_b200 reader involved
+    assert str(table.schema.field("input_features").type).startswith("extension<arrow.fixed_shape_tensor")
+    feats = table.column("input_features").combine_chunks().to_numpy_ndarray()
+    labels = table.column("labels").combine_chunks().to_numpy_ndarray()
+    assert feats.shape == (6, 128, 3000) and labels.shape == (6, 448)
+    out = ref.collate_parquet({"input_features": [np.array(x) for x in feats], "labels": [np.array(x) for x in labels]})
+    assert out["input_features"].dtype == torch.float32 and out["labels"].dtype == torch.int64
+    assert torch.equal(out["input_features"], torch.from_numpy(b["input_features"]))
+    assert torch.equal(out["labels"], torch.from_numpy(b["labels"]))
