@@ -183,6 +183,7 @@ int launch_tc(wfe_handle* h, const void* pcm, int pcm_dtype, float scale, const 
   p.out = out;
   p.mask = mask;
   p.tile_key = reinterpret_cast<uint32_t*>(scratch);
+  p.tile_min = p.tile_key + (size_t)batch * wfe::tc::kNTiles;  // (the scratch is sized for the CUDA-core kernel's 94 tiles per clip)
   p.b_mat = h->d_tc_b;
   p.tw = h->d_tc_tw;
   p.pcm_scale = scale;
@@ -210,11 +211,18 @@ int launch_tc(wfe_handle* h, const void* pcm, int pcm_dtype, float scale, const 
     if (cr != CUDA_SUCCESS) return fail(WFE_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)cr) + ")");
   }
   if (!tma_ok && pcm_dtype == WFE_PCM_F32) p.pcm_dtype = 3;  // float32 at an odd address: generic staging only
-  WFE_CUDA(cudaMemsetAsync(scratch, 0, scratch_bytes(h, batch), st));
+  // (every tile word is written by the main kernel before the clamp pass reads it: only the error word needs clearing)
+  WFE_CUDA(cudaMemsetAsync(p.tile_key + (size_t)batch * h->ntiles, 0, 4 * sizeof(uint32_t), st));
   long long grid = h->sm_count;
   if (grid > total) grid = total;
   wfe::tc::logmel_tc_kernel<OutT, kNMel><<<(unsigned)grid, wfe::tc::kThreads, wfe::tc::kSmemBytes, st>>>(p, tmap, err_flag);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
+  WFE_CUDA(cudaGetLastError());
+  // second pass: the per-clip clamp, over the tiles that have something below their clip's floor (often none)
+  long long cgrid = (long long)h->sm_count * 8;
+  if (cgrid > total) cgrid = total;
+  wfe::tc::clamp_kernel<OutT><<<(unsigned)cgrid, wfe::tc::kClampThreads, 0, st>>>(
+      reinterpret_cast<OutT*>(out), p.tile_key, p.tile_min, kNMel, (uint32_t)total);
+  g_launches.fetch_add(2, std::memory_order_relaxed);
   WFE_CUDA(cudaGetLastError());
   return WFE_OK;
 }
@@ -225,13 +233,24 @@ __global__ void cast_kernel(const float* __restrict__ src, OutT* __restrict__ ds
     dst[i] = wfe::tc::to_out<OutT>(src[i]);
 }
 
+// The kernel re-partitions its registers with setmaxnreg; the budget (wfe_logmel_tc.cuh: kRegs*) assumes that it was
+// compiled to launch with exactly kRegsLaunch registers per thread -- a mismatch would hang, so it is checked here.
+template <typename OutT, int kNMel>
+int prepare_tc_kernel() {
+  WFE_CUDA(cudaFuncSetAttribute(wfe::tc::logmel_tc_kernel<OutT, kNMel>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)wfe::tc::kSmemBytes));
+  cudaFuncAttributes fa;
+  WFE_CUDA(cudaFuncGetAttributes(&fa, wfe::tc::logmel_tc_kernel<OutT, kNMel>));
+  if (fa.numRegs != wfe::tc::kRegsLaunch)
+    return fail(WFE_ERR_UNSUPPORTED, "tensor-core kernel compiled with " + std::to_string(fa.numRegs) +
+                                         " registers per thread, its setmaxnreg budget needs " +
+                                         std::to_string(wfe::tc::kRegsLaunch));
+  return WFE_OK;
+}
 template <typename OutT>
 int prepare_tc_kernels() {
-  WFE_CUDA(cudaFuncSetAttribute(wfe::tc::logmel_tc_kernel<OutT, 80>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)wfe::tc::kSmemBytes));
-  WFE_CUDA(cudaFuncSetAttribute(wfe::tc::logmel_tc_kernel<OutT, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)wfe::tc::kSmemBytes));
-  return WFE_OK;
+  const int rc = prepare_tc_kernel<OutT, 80>();
+  return rc != WFE_OK ? rc : prepare_tc_kernel<OutT, 128>();
 }
 
 int logmel_dispatch(wfe_handle* h, const void* pcm, int pcm_dtype, float scale, const int64_t* offsets,
@@ -421,9 +440,7 @@ int setup_tensor_core_path(wfe_handle* h, const float* mel_filters) {
   WFE_CUDA(cudaMemcpy(h->d_tc_b, bmat.data(), kBBytes, cudaMemcpyHostToDevice));
   WFE_CUDA(cudaMemcpy(h->d_tc_tw, tw.data(), kTwBytes, cudaMemcpyHostToDevice));
 #ifdef WFE_EXP_MINIMAL
-  WFE_CUDA(cudaFuncSetAttribute(wfe::tc::logmel_tc_kernel<float, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)wfe::tc::kSmemBytes));
-  int rc = WFE_OK;
+  int rc = prepare_tc_kernel<float, 128>();
 #else
   int rc = prepare_tc_kernels<float>();
   if (rc == WFE_OK) rc = prepare_tc_kernels<__half>();
@@ -449,6 +466,15 @@ int wfe_debug_read_trace(unsigned long long* dst, int n) {
 // timing-trace build only (not part of the shipped ABI)
 int wfe_debug_read_tc_trace(unsigned long long* dst, int n) {
   return (int)cudaMemcpyFromSymbol(dst, wfe::tc::g_tc_trace, sizeof(unsigned long long) * n);
+}
+int wfe_debug_read_tc_warps(unsigned long long* dst) {
+  return (int)cudaMemcpyFromSymbol(dst, wfe::tc::g_tc_warps, sizeof(unsigned long long) * 128);
+}
+int wfe_debug_read_tc_cta(unsigned long long* dst) {
+  return (int)cudaMemcpyFromSymbol(dst, wfe::tc::g_tc_cta, sizeof(unsigned long long) * 160 * 4);
+}
+int wfe_debug_read_tc_tiles(unsigned long long* dst) {
+  return (int)cudaMemcpyFromSymbol(dst, wfe::tc::g_tc_tiles, sizeof(unsigned long long) * 3 * 64);
 }
 #endif
 

@@ -38,8 +38,7 @@
 //                         (generated straight-line code), log10, (x+4)/4, store, tile min/max
 //   warp  8     MMA       one elected lane issues 3 tcgen05.mma per (k-step, n1) slot, commits to mbarriers
 //   warp  9     LOADER    one TMA per tile
-//   warp 10     CLAMP     per-clip max-8 clamp books (same scheme as wfe_logmel.cuh: one published key per tile, fix-ups
-//                         of this CTA's own tiles from L2 once their clip is complete)
+//   warp 14     BOOKS     publishes each tile's maximum and minimum for the clamp pass (clamp_kernel)
 // Specialised for n_samples = 480000 (3000 frames), n_mel in {80, 128} with the slaney structure baked by
 // tools/gen_tc_epilogue.py; everything else runs on the CUDA-core kernel.
 #pragma once
@@ -69,10 +68,22 @@ constexpr int kN = 112;                           // MMA N: 52 k2 x (re, im) = 1
 constexpr int kBChunkBytes = kN * 16;             // 1792
 constexpr int kBBytes = 2 * 14 * kBChunkBytes;    // [hi/lo][chunk 14][n 112][16 B] = 50176
 constexpr int kTwBytes = 26 * 3 * 16;             // [pair][n1-1] (cos_k2, cos_k2+1, sin_k2, sin_k2+1)
-constexpr int kThreads = 11 * 32;
+constexpr int kThreads = 16 * 32;                // 8 epilogue workers, 4 prep workers, MMA issuer, loader, clamp books, 1 idle
+// register budget (setmaxnreg).  The kernel launches with 128 registers per thread (16 warp slots x 32 x 128 = the whole
+// file; the host checks the compiled count); a warp can only grow into what the warps of its OWN scheduler (warp index
+// mod 4) gave back: per scheduler 2 x kRegsE + kRegsP + kRegsH <= 4 x 128.
+#ifndef WFE_TC_REGS_E
+#define WFE_TC_REGS_E 168
+#define WFE_TC_REGS_P 104
+#define WFE_TC_REGS_H 56
+#endif
+constexpr int kRegsLaunch = 128, kRegsE = WFE_TC_REGS_E, kRegsP = WFE_TC_REGS_P, kRegsH = WFE_TC_REGS_H;
+#ifndef WFE_TC_REGS_PROBE
+static_assert(2 * kRegsE + kRegsP + kRegsH <= 4 * kRegsLaunch, "register budget of an SM sub-partition");
+#endif
 constexpr int kTmemCols = 512;
 constexpr int kTmemA = 4 * kN;                    // columns 448..511: A slots, 16 columns per n1 (8 hi + 8 lo)
-constexpr int kRing = 16;   // pending-tile ring of the clamp warp (a clip completes within about one tile iteration)
+constexpr int kWarpMma = 12, kWarpLoad = 13, kWarpClamp = 14;
 constexpr int kRawBoxBytes = kRawRows * kRawPitch * 4;              // 85280: what one TMA delivers
 constexpr int kRawBufBytes = (kRawBoxBytes + 127) & ~127;           // 85376: TMA destinations are 128-byte aligned
 
@@ -96,18 +107,31 @@ constexpr size_t kSmemBytes = kSmemWs + 2 * kWsFloats * 4;           // 225760 (
 #undef WFE_TC_GEN_COUNTS
 constexpr int kMaxShared = kTcShared80 > kTcShared128 ? kTcShared80 : kTcShared128;  // filters fed by both epilogue halves
 
+#ifndef WFE_TC_TRACE_CTA
+#define WFE_TC_TRACE_CTA 0
+#endif
 #ifdef WFE_TC_TRACE
 // timing-trace build (diagnostics only): CTA 0 stamps clock64() at role milestones of its tile iterations 4..11
-constexpr int kTrTiles = 8, kTrRoles = 5, kTrPts = 32;
+constexpr int kTrTiles = 8, kTrRoles = 8, kTrPts = 64;
 __device__ unsigned long long g_tc_trace[kTrTiles * kTrRoles * kTrPts];
+__device__ unsigned long long g_tc_tiles[3][64];  // tile start stamps of CTA 0, 77, 147 ([63] kernel start, [62] workers done, [61..59] helpers done)
+__device__ unsigned long long g_tc_warps[16][8];
+__device__ unsigned long long g_tc_cta[160][4];  // per CTA: smid, tiles done, first tile start, workers done
 #define TCT(role, it, pt)                                                                      \
   do {                                                                                         \
     if (blockIdx.x == 0 && (it) >= 4 && (it) < 4 + kTrTiles)                                   \
       g_tc_trace[(((it) - 4) * kTrRoles + (role)) * kTrPts + (pt)] = clock64();                \
   } while (0)
+#define TCW(i)                                                                     \
+  do {                                                                             \
+    if (blockIdx.x == WFE_TC_TRACE_CTA && nt == 6 && lane == 0) g_tc_warps[warp][i] = clock64();  \
+  } while (0)
 #else
 #define TCT(role, it, pt) \
   do {                    \
+  } while (0)
+#define TCW(i) \
+  do {         \
   } while (0)
 #endif
 
@@ -118,7 +142,8 @@ struct TcParams {
   const float2* norm;
   void* out;                // (B, n_mel, 3000), element type = template OutT
   int32_t* mask;
-  uint32_t* tile_key;       // [B][24]
+  uint32_t* tile_key;       // [B][24] key of each tile's maximum (f2key)
+  uint32_t* tile_min;       // [B][24] float bits of each tile's minimum, or kMinSilent
   const uint4* b_mat;       // kBBytes: DFT-100 operand, canonical layout, hi then lo
   const float4* tw;         // kTwBytes: twiddles W400^(n1 k2)
   float pcm_scale;
@@ -138,6 +163,14 @@ __device__ __forceinline__ float load_pcm(const void* pcm, int dtype, int64_t i,
 // PTX wrappers
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <int N>
+__device__ __forceinline__ void reg_grow() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void reg_shrink() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -164,36 +197,34 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
 #ifndef WFE_TC_WAIT
 #define WFE_TC_WAIT 1  // 0: bare try_wait spin, 1: try_wait with a suspend-time hint, 2: nanosleep back-off between polls
 #endif
-// Waits for the phase with the given parity.  The fast path is one try_wait; the slow path is out of line (the kernel's
-// straight-line code is instruction-cache bound: ~40 inlined copies of the loop cost 25 KB) and gives up after a few
-// seconds, so that a protocol bug turns into a wrong answer + error flag instead of a hung GPU.
-__device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t parity, uint32_t* err_flag) {
-  const long long t0 = clock64();
-#pragma unroll 1
-  for (uint32_t spin = 0;; ++spin) {
-    uint32_t ok;
-#if WFE_TC_WAIT == 2
-    __nanosleep(40);
+// Waits for the phase with the given parity.  Inline on purpose: a real call inside a role whose register count was
+// changed by setmaxnreg makes ptxas give up ("register allocation failed").  The loop is a handful of instructions:
+// try_wait suspends the thread for a hardware time slice (hint: 4 us) and is woken by the phase completing.  It gives
+// up after ~4 M probes, so that a protocol bug turns into a wrong answer + error flag instead of a hung GPU.
+#ifndef WFE_TC_SLEEP_SHORT
+#define WFE_TC_SLEEP_SHORT 32   // ns between probes of a latency-critical wait (operand slots, accumulators)
+#define WFE_TC_SLEEP_LONG 256   // ns between probes of a wait that is a tile long (raw buffers, clamp books)
 #endif
+template <int kSleepNs = WFE_TC_SLEEP_SHORT>
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t* err_flag) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-#if WFE_TC_WAIT == 1
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 4000;\n\t"
-#else
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-#endif
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar_addr), "r"(parity)
+        : "r"(addr), "r"(parity)
         : "memory");
     if (ok) return;
-    if ((spin & 1023u) == 1023u && clock64() - t0 > 6000000000ll) break;
+    // a probing warp takes issue slots from the warps that share its scheduler (measured: a bare probe loop costs the
+    // workers a third of theirs); a sleeping warp takes none
+    if (kSleepNs > 0) __nanosleep(kSleepNs);
+    if (++spins > (1u << 22)) break;
   }
   if (err_flag != nullptr) atomicExch(err_flag, 0xDEADu);
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t* err_flag) {
-  if (mbar_try(bar, parity)) return;
-  mbar_wait_slow(smem_u32(bar), parity, err_flag);
 }
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -291,12 +322,14 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
 // ---------------------------------------------------------------------------------------------------------------
 // tile geometry: every role derives it from the tile id alone
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kModeAsyncHead = 3, kModeDone = -1;
+constexpr int kModeAsyncHead = 3, kModeAsyncTail = 4, kModeDone = -1;
+__device__ __forceinline__ bool is_tma_mode(int mode) { return mode == kModeAsync || mode == kModeAsyncHead || mode == kModeAsyncTail; }
 struct Tile {
-  int b, tile, len, mode;  // mode: kModeSilent / kModeAsync (TMA) / kModeAsyncHead (TMA + reflect patch) / kModeSync (generic)
+  int b, tile, len, mode;  // kModeSilent / kModeAsync (TMA) / kModeAsyncHead, kModeAsyncTail (TMA + patch by the loader) / kModeSync (generic)
   int64_t off;
 };
-__device__ __forceinline__ Tile tile_info(const TcParams& p, uint32_t id) {
+// `extent` = one past the last PCM element of the whole batch (only the loader knows it; 0 = do not classify tail tiles)
+__device__ __forceinline__ Tile tile_info(const TcParams& p, uint32_t id, int64_t extent = 0) {
   Tile t;
   t.b = (int)(id / (uint32_t)kNTiles);
   t.tile = (int)(id - (uint32_t)t.b * (uint32_t)kNTiles);
@@ -319,14 +352,26 @@ __device__ __forceinline__ Tile tile_info(const TcParams& p, uint32_t id) {
     //  does, the TMA fills out-of-range coordinates with zeros -- and are overwritten by the reflect pad afterwards)
     //  -- provided the clip does not start the buffer: the TMA bounds-checks the COORDINATE, not the address, and would
     //  zero-fill the head of every row whose column coordinate is negative)
-    const bool bulk = p.pcm_dtype == 0 && p.norm == nullptr && (s_begin >= 0 || t.tile == 0) &&
-                      s_begin + (kRawRows - 1) * kHop + kRawPitch <= t.len &&
-                      (reinterpret_cast<uintptr_t>(src) & 15u) == 0 && t.off + s_begin < (int64_t)0x7fff0000 &&
-                      t.off + s_begin >= 0;
-    t.mode = bulk ? (s_begin >= 0 ? kModeAsync : kModeAsyncHead) : kModeSync;
+    const bool base_ok = p.pcm_dtype == 0 && p.norm == nullptr && (s_begin >= 0 || t.tile == 0) &&
+                         (reinterpret_cast<uintptr_t>(src) & 15u) == 0 && t.off + s_begin < (int64_t)0x7fff0000 &&
+                         t.off + s_begin >= 0;
+    const int box_end = s_begin + (kRawRows - 1) * kHop + kRawPitch;
+    if (base_ok && box_end <= t.len)
+      t.mode = s_begin >= 0 ? kModeAsync : kModeAsyncHead;
+    else if (base_ok && s_begin >= 0 && t.off + box_end <= extent)
+      // the tile that straddles the end of its clip: the box is still inside the caller's buffer (it reads into whatever
+      // follows the clip), and the loader overwrites everything from the clip's end on (zeros / the reflect pad)
+      t.mode = kModeAsyncTail;
+    else
+      t.mode = kModeSync;
   }
   return t;
 }
+
+// The CTA's i-th tile: row i of gridDim.x consecutive tile ids (clip-major: the CTAs work on the same few clips at any
+// time), column rotated by i, so that every CTA meets every tile-in-clip position -- clip heads and tails cost more than
+// interior tiles -- equally often.  A value >= total_tiles means "no tile in this (last, short) row".
+__device__ __forceinline__ uint32_t cta_tile(uint32_t i) { return i * gridDim.x + (blockIdx.x + i) % gridDim.x; }
 
 template <typename OutT>
 __device__ __forceinline__ OutT to_out(float v);
@@ -345,59 +390,69 @@ __device__ __forceinline__ float from_out<__half>(__half v) { return __half2floa
 template <>
 __device__ __forceinline__ float from_out<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 
-// per-clip clamp applied to one 128-frame tile of this CTA by ONE warp: lane owns 4 consecutive frames of a mel row,
-// 8 rows in flight.  silent: store the constant without reading.
+// ---------------------------------------------------------------------------------------------------------------
+// Per-clip clamp max(x, max - 8) as a second, HBM-speed pass over the tiles that need it.
+// The main kernel stores unclamped values and publishes, per tile, the key of its maximum (tile_key) and the bits of its
+// minimum (tile_min; kMinSilent = the tile lies wholly in the zero padding and was not written at all).  A clip's floor
+// is known once all its tiles are: this kernel takes it from the 24 keys, skips every tile whose minimum is already above
+// it (white noise: all of them), rewrites only the elements below it elsewhere, and fills padding tiles with the constant.
+// (Round 1 and the first tensor-core versions fixed tiles up inside the main kernel, from L2, by one warp per CTA: that
+//  couples the CTAs -- a pending ring that fills up stalls a fast CTA behind a slow one -- and on speech-like audio the
+//  one warp became the bottleneck: 15.0 M audio-s/s against 21.1 M on noise.)
+// ---------------------------------------------------------------------------------------------------------------
+constexpr uint32_t kMinSilent = 0x7fc00001u;
+constexpr int kClampThreads = 256;
 template <typename OutT>
-__device__ __forceinline__ void fix_tile_tc(OutT* __restrict__ out, int n_mel, int b, int tile, float fl, bool silent,
-                                            int lane) {
-  const int t0 = tile * kTileM;
-  const int nvalid = min(kTileM, kNFrames - t0);  // multiple of 4 (3000 = 23 * 128 + 56)
-  if (4 * lane >= nvalid) return;
+__global__ void __launch_bounds__(kClampThreads)
+    clamp_kernel(OutT* __restrict__ out, const uint32_t* __restrict__ tile_key, const uint32_t* __restrict__ tile_min,
+                 int n_mel, uint32_t total_tiles) {
   using Vec = typename std::conditional<sizeof(OutT) == 4, float4, uint2>::type;
-  OutT* const base = out + (size_t)b * n_mel * kNFrames + t0 + 4 * lane;
-  OutT cv[4];
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (uint32_t id = blockIdx.x; id < total_tiles; id += gridDim.x) {
+    const int b = (int)(id / (uint32_t)kNTiles), tile = (int)(id - (uint32_t)b * (uint32_t)kNTiles);
+    uint32_t k = lane < kNTiles ? __ldg(tile_key + (size_t)b * kNTiles + lane) : 0u;
+    k = __reduce_max_sync(0xffffffffu, k);
+    const float fl = fmaxf(key2f(k) - 2.0f, -1.5f);
+    const uint32_t mb = __ldg(tile_min + id);
+    const bool silent = mb == kMinSilent;
+    if (!silent && !(__uint_as_float(mb) < fl)) continue;  // nothing below the floor in this tile
+    const int t0 = tile * kTileM;
+    const int nvalid = min(kTileM, kNFrames - t0);  // multiple of 4 (3000 = 23 * 128 + 56)
+    const int fq = tid & 31, r0 = tid >> 5;         // 4 frames per thread, 8 rows per pass
+    if (4 * fq >= nvalid) continue;
+    OutT* const base = out + (size_t)b * n_mel * kNFrames + t0 + 4 * fq;
+    OutT cv[4];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) cv[e] = to_out<OutT>(fl);
-  const Vec cvec = *reinterpret_cast<const Vec*>(cv);
-  constexpr int kDeep = 16;  // rows in flight: one warp has to keep up with a fix-up per tile on speech-like audio
-  for (int m0 = 0; m0 < n_mel; m0 += kDeep) {
-    if (silent) {
+    for (int e = 0; e < 4; ++e) cv[e] = to_out<OutT>(fl);
+    const Vec cvec = *reinterpret_cast<const Vec*>(cv);
+    constexpr int kDeep = 8;  // rows in flight per thread
+    for (int m0 = r0; m0 < n_mel; m0 += 8 * kDeep) {
+      if (silent) {
 #pragma unroll
-      for (int j = 0; j < kDeep; ++j)
-        if (m0 + j < n_mel) *reinterpret_cast<Vec*>(base + (size_t)(m0 + j) * kNFrames) = cvec;
-    } else {
-      Vec v[kDeep];
+        for (int j = 0; j < kDeep; ++j)
+          if (m0 + 8 * j < n_mel) *reinterpret_cast<Vec*>(base + (size_t)(m0 + 8 * j) * kNFrames) = cvec;
+      } else {
+        Vec v[kDeep];
 #pragma unroll
-      for (int j = 0; j < kDeep; ++j)
-        if (m0 + j < n_mel) v[j] = __ldcg(reinterpret_cast<const Vec*>(base + (size_t)(m0 + j) * kNFrames));
+        for (int j = 0; j < kDeep; ++j)
+          if (m0 + 8 * j < n_mel) v[j] = __ldcs(reinterpret_cast<const Vec*>(base + (size_t)(m0 + 8 * j) * kNFrames));
 #pragma unroll
-      for (int j = 0; j < kDeep; ++j) {
-        if (m0 + j >= n_mel) continue;
-        OutT e[4];
-        *reinterpret_cast<Vec*>(e) = v[j];
-        bool need = false;
+        for (int j = 0; j < kDeep; ++j) {
+          if (m0 + 8 * j >= n_mel) continue;
+          OutT e[4];
+          *reinterpret_cast<Vec*>(e) = v[j];
+          bool need = false;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float f = from_out<OutT>(e[k]);
-          if (f < fl) {  // (-inf, the log of a zero mel power, is below every floor)
-            need = true;
-            e[k] = cv[k];
+          for (int q = 0; q < 4; ++q) {
+            if (from_out<OutT>(e[q]) < fl) {  // (-inf, the log of a zero mel power, is below every floor)
+              need = true;
+              e[q] = cv[q];
+            }
           }
+          if (need) *reinterpret_cast<Vec*>(base + (size_t)(m0 + 8 * j) * kNFrames) = *reinterpret_cast<const Vec*>(e);
         }
-        if (need) *reinterpret_cast<Vec*>(base + (size_t)(m0 + j) * kNFrames) = *reinterpret_cast<const Vec*>(e);
       }
     }
-  }
-}
-
-__device__ __forceinline__ float wait_clip_floor_tc(const uint32_t* tile_key, int b, int lane) {
-  const uint32_t* row = tile_key + (size_t)b * kNTiles;
-  for (;;) {
-    uint32_t k = lane < kNTiles ? ld_relaxed_u32(row + lane) : 1u;
-    const bool zero = __any_sync(0xffffffffu, k == 0);
-    k = __reduce_max_sync(0xffffffffu, k);
-    if (!zero) return fmaxf(key2f(k) - 2.0f, -1.5f);
-    __nanosleep(200);
   }
 }
 
@@ -450,6 +505,25 @@ __device__ __forceinline__ float raw_absmax_slice(const float* raw, int t, int n
   }
   return mx;
 }
+// the same as a compact loop over all 5180 float4 of a tile (four loads in flight)
+__device__ __forceinline__ uint32_t raw_absmax_rolled(const float* raw, int t, int nthreads) {
+  float mx = 0.f;
+  constexpr int kQuads = ((kRawRows - 1) * kHop + (kRawLen - (kRawRows - 1) * kHop)) / 4;
+#pragma unroll 1
+  for (int i0 = t; i0 < kQuads; i0 += 4 * nthreads) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = min(i0 + u * nthreads, kQuads - 1);  // (re-reading the last element is harmless)
+      const int r = i / (kHop / 4);
+      v[u] = *reinterpret_cast<const float4*>(raw + r * kRawPitch + 4 * (i - r * (kHop / 4)));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v[u].x), fabsf(v[u].y)), fmaxf(fabsf(v[u].z), fabsf(v[u].w))));
+  }
+  return __float_as_uint(mx);
+}
 // scaled window table (exact: the scale is a power of two), zero beyond the 400-point frame
 __device__ __forceinline__ void write_ws(float* ws, float scale, int t, int nthreads) {
   for (int i = t; i < kWsFloats / 4; i += nthreads) {
@@ -459,6 +533,65 @@ __device__ __forceinline__ void write_ws(float* ws, float scale, int t, int nthr
                                                    __uint_as_float(w.z) * scale, __uint_as_float(w.w) * scale);
   }
 }
+
+// One whole k-step (16 n2 = 64 consecutive samples, all four n1) of this thread's frame: window, split into fp16 hi / lo.
+// xrow = the frame's first sample in the raw buffer, ws = the buffer's scaled window.  Two float4 of samples give, for
+// every n1, one packed fp16x2 word of hi parts and one of lo parts (the 32 samples of a half k-step never straddle a
+// hop row: 160 = 5 x 32).
+__device__ __forceinline__ void prep_kstep_regs(const float* xrow, const float* ws, int j, uint32_t (&hv)[4][8],
+                                                uint32_t (&lv)[4][8]) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const int n0 = 64 * j + 32 * c;
+    const float* xp = xrow + n0 + (kRawPitch - kHop) * ((n0 >= kHop ? 1 : 0) + (n0 >= 2 * kHop ? 1 : 0));
+    const float* wp = ws + n0;
+#pragma unroll
+    for (int q2 = 0; q2 < 4; ++q2) {
+      float h[4][2], l[4][2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const float4 x = *reinterpret_cast<const float4*>(xp + 8 * q2 + 4 * q);
+        const float4 w = *reinterpret_cast<const float4*>(wp + 8 * q2 + 4 * q);
+        const float y[4] = {x.x * w.x, x.y * w.y, x.z * w.z, x.w * w.w};
+#pragma unroll
+        for (int n1 = 0; n1 < 4; ++n1) {
+          const float hb = __uint_as_float(__float_as_uint(y[n1]) & 0xFFFFE000u);  // 11 significant bits: exact in fp16
+          h[n1][q] = hb;
+          l[n1][q] = y[n1] - hb;
+        }
+      }
+#pragma unroll
+      for (int n1 = 0; n1 < 4; ++n1) {
+        hv[n1][4 * c + q2] = pack_h2(h[n1][0], h[n1][1]);
+        lv[n1][4 * c + q2] = pack_h2(l[n1][0], l[n1][1]);
+      }
+    }
+  }
+}
+// Hand one k-step to the tensor core, slot by slot (slot = n1).  A slot is free once the MMAs of the PREVIOUS k-step
+// have read it: their commit arrives on `empty[n1]`, a barrier that completes exactly once per tile, so `parity` (the
+// tile's) is unambiguous whichever warp deposits.
+__device__ __forceinline__ void deposit_kstep(uint64_t* empty, uint32_t parity, uint64_t* full, uint32_t a_slot0,
+                                              const uint32_t (&hv)[4][8], const uint32_t (&lv)[4][8], uint32_t* err_flag) {
+#pragma unroll
+  for (int n1 = 0; n1 < 4; ++n1) {
+    mbar_wait(&empty[n1], parity, err_flag);
+    tc_fence_after();
+    const uint32_t r[16] = {hv[n1][0], hv[n1][1], hv[n1][2], hv[n1][3], hv[n1][4], hv[n1][5], hv[n1][6], hv[n1][7],
+                            lv[n1][0], lv[n1][1], lv[n1][2], lv[n1][3], lv[n1][4], lv[n1][5], lv[n1][6], lv[n1][7]};
+    tmem_st16(a_slot0 + 16 * n1, r);
+    tmem_st_wait();
+    tc_fence_before();
+    mbar_arrive(&full[n1]);
+  }
+}
+
+// named barriers: 1 the epilogue workers' own; 2..5 the epilogue's partial-sum exchange (one per lane quarter); 8 "tile
+// 0's window table is ready" (epilogue workers arrive, prep workers wait); 9 the prep workers' own.  (The per-tile hand-
+// shakes between the two groups are mbarriers: a named barrier would make the early epilogue warps wait for the late ones.)
+__device__ __forceinline__ void bar_arrive_n(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_sync_n(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+constexpr int kBarWs0 = 8, kBarPrep = 9, kBarBoth = 384;
 
 // named barrier among the 256 worker threads
 __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -474,20 +607,21 @@ __global__ void __launch_bounds__(kThreads, 1)
   const float4* const tw_sm = reinterpret_cast<const float4*>(smem + kSmemTw);
   float* const ws_sm = reinterpret_cast<float*>(smem + kSmemWs);  // [2 raw buffers][448]
 
-  __shared__ uint64_t bar_raw_full[2], bar_raw_empty[2], bar_meta_full[2], bar_a_full[4], bar_a_empty[2][4], bar_d_full,
-      bar_d_empty, bar_st_full[2], bar_st_empty[2];
+  __shared__ uint64_t bar_raw_full[2], bar_raw_empty[2], bar_meta_full[2], bar_a_full[4], bar_a_empty[kKSteps][4], bar_d_full,
+      bar_d_empty, bar_st_full[2], bar_st_empty[2], bar_ws, bar_staged;
   __shared__ TileMeta s_meta[2];        // loader -> workers: geometry, scale and log-domain constant of the tile in buffer rb
   __shared__ uint32_t s_tmem;
   __shared__ uint32_t s_pmax[8];        // generic staging: per-warp max |x| bits
   __shared__ uint32_t s_tilemax[2];     // per raw buffer: max |x| bits of the tile (atomicMax by the worker warps)
+  __shared__ float2 s_scale[2];         // per raw buffer: (power-of-two scale, log-domain constant) of the tile
   __shared__ float s_red[2][2][8];      // [tile parity][max, min][worker warp] of y over the warp's share of the tile
   __shared__ float s_part[(kNMel == 128 ? kTcShared128 : kTcShared80) * kTileM];  // epilogue half 1 -> half 0: partial sums of the shared mel filters
-  __shared__ int2 s_pend_bt[kRing];
-  __shared__ float2 s_pend_mm[kRing];
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform: role branches do not diverge
 #ifdef WFE_TC_TRACE
+  if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 77 || blockIdx.x == 147))
+    g_tc_tiles[blockIdx.x == 0 ? 0 : (blockIdx.x == 77 ? 1 : 2)][63] = clock64();
   if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 77)) {  // whole-kernel span of two CTAs: SM clock and wall clock
     unsigned long long gt;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
@@ -503,29 +637,31 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bar_raw_full[s], 1);
-      mbar_init(&bar_raw_empty[s], 256);
+      mbar_init(&bar_raw_empty[s], 384);
       mbar_init(&bar_meta_full[s], 1);
       mbar_init(&bar_st_full[s], 8);
       mbar_init(&bar_st_empty[s], 1);
     }
     for (int s = 0; s < 4; ++s) {
       mbar_init(&bar_a_full[s], 128);
-      mbar_init(&bar_a_empty[0][s], 1);
-      mbar_init(&bar_a_empty[1][s], 1);
+      for (int j = 0; j < kKSteps; ++j) mbar_init(&bar_a_empty[j][s], 1);
     }
+    mbar_init(&bar_ws, 128);      // prep workers: the next tile's window table and scale are ready
+    mbar_init(&bar_staged, 256);  // epilogue workers: an edge tile (if any) has been staged
     mbar_init(&bar_d_full, 1);
     mbar_init(&bar_d_empty, 256);
     s_tilemax[0] = s_tilemax[1] = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 9) tmem_alloc(&s_tmem, kTmemCols);
+  if (warp == kWarpLoad) tmem_alloc(&s_tmem, kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s_tmem;
 
   if (warp < 8) {
-    // =========================================== WORKERS ===========================================
+    // ====================================== EPILOGUE WORKERS ======================================
+    reg_grow<kRegsE>();
     const int qt = warp & 3;                 // TMEM lane quarter: lanes 32 qt .. 32 qt + 31
     const int hh = warp >> 2;                // which of the quarter's two warps
     const int m = qt * 32 + lane;            // frame within the tile == TMEM lane
@@ -609,127 +745,81 @@ __global__ void __launch_bounds__(kThreads, 1)
       mx = max(max(max(s_pmax[0], s_pmax[1]), max(s_pmax[2], s_pmax[3])), max(max(s_pmax[4], s_pmax[5]), max(s_pmax[6], s_pmax[7])));
       scale_from_max(mx, tm.scale, tm.tile_k);
       write_ws(ws_sm + rb * kWsFloats, tm.scale, wt, 256);
+      if (wt == 0) s_scale[rb] = make_float2(tm.scale, tm.tile_k);
       worker_bar();  // ws complete; s_pmax free for the next staged tile
-    };
-
-    // one k-step (16 n2 = 64 consecutive samples, all four n1) of the tile in raw buffer rb: window, split into fp16
-    // hi / lo, and hand the four operand slots to the tensor core as they become free.  kj = running k-step index.
-    auto prep_kstep = [&](uint32_t rb, int j, uint32_t kj) {
-      const float* const xrow = reinterpret_cast<const float*>(smem + kSmemRaw + rb * kRawBufBytes) + m * kRawPitch;
-      const float* const ws = ws_sm + rb * kWsFloats;
-      uint32_t hv[4][8], lv[4][8];  // per n1: 16 fp16 hi (K order), 16 fp16 lo
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        // the 32 samples of a half k-step never straddle a hop row (160 = 5 x 32)
-        const int n0 = 64 * j + 32 * c;
-        const float* xp = xrow + n0 + (kRawPitch - kHop) * ((n0 >= kHop ? 1 : 0) + (n0 >= 2 * kHop ? 1 : 0));
-        const float* wp = ws + n0;
-        float h[4][8], l[4][8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 x = *reinterpret_cast<const float4*>(xp + 4 * q);
-          const float4 w = *reinterpret_cast<const float4*>(wp + 4 * q);
-          const float y[4] = {x.x * w.x, x.y * w.y, x.z * w.z, x.w * w.w};
-#pragma unroll
-          for (int n1 = 0; n1 < 4; ++n1) {
-            const float hb = __uint_as_float(__float_as_uint(y[n1]) & 0xFFFFE000u);  // 11 significant bits: exact in fp16
-            h[n1][q] = hb;
-            l[n1][q] = y[n1] - hb;
-          }
-        }
-#pragma unroll
-        for (int n1 = 0; n1 < 4; ++n1)
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            hv[n1][4 * c + u] = pack_h2(h[n1][2 * u], h[n1][2 * u + 1]);
-            lv[n1][4 * c + u] = pack_h2(l[n1][2 * u], l[n1][2 * u + 1]);
-          }
-      }
-      // The MMAs of k-step kj - 1 have read a slot when their commit arrives.  Commits go to the barrier set of THAT
-      // k-step's parity: a parity wait cannot tell phase i from phase i + 2, and with the quarter's two warps
-      // alternating k-steps a single set would let a warp run two phases ahead.  This way each warp consumes every
-      // phase of "its" set.
-      const uint32_t par = hh ? ((kj >> 1) & 1u) : (((kj >> 1) & 1u) ^ 1u);
-#if WFE_TC_DEPOSIT == 1
-      // slots in two groups of two: one tcgen05.wait::st per group instead of per slot
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-#pragma unroll
-        for (int n1 = 2 * g; n1 < 2 * g + 2; ++n1) {
-          mbar_wait(&bar_a_empty[hh ^ 1][n1], par, err_flag);
-          tc_fence_after();
-          const uint32_t r[16] = {hv[n1][0], hv[n1][1], hv[n1][2], hv[n1][3], hv[n1][4], hv[n1][5], hv[n1][6], hv[n1][7],
-                                  lv[n1][0], lv[n1][1], lv[n1][2], lv[n1][3], lv[n1][4], lv[n1][5], lv[n1][6], lv[n1][7]};
-          tmem_st16(a_slot0 + 16 * n1, r);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&bar_a_full[2 * g]);
-        mbar_arrive(&bar_a_full[2 * g + 1]);
-      }
-#else
-#pragma unroll
-      for (int n1 = 0; n1 < 4; ++n1) {
-        mbar_wait(&bar_a_empty[hh ^ 1][n1], par, err_flag);
-        tc_fence_after();
-        const uint32_t r[16] = {hv[n1][0], hv[n1][1], hv[n1][2], hv[n1][3], hv[n1][4], hv[n1][5], hv[n1][6], hv[n1][7],
-                                lv[n1][0], lv[n1][1], lv[n1][2], lv[n1][3], lv[n1][4], lv[n1][5], lv[n1][6], lv[n1][7]};
-        tmem_st16(a_slot0 + 16 * n1, r);
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&bar_a_full[n1]);
-      }
-#endif
     };
 
     // scale + scaled window of a TMA tile whose maximum the workers have accumulated in s_tilemax[rb] (all workers,
     // after a worker_bar that ordered the atomics); resets the accumulator for the buffer's next tile
     auto finish_scale = [&](uint32_t rb, TileMeta& tm) {
-      if (tm.mode == kModeAsync || tm.mode == kModeAsyncHead) {
+      if (is_tma_mode(tm.mode)) {
         scale_from_max(s_tilemax[rb], tm.scale, tm.tile_k);
         write_ws(ws_sm + rb * kWsFloats, tm.scale, wt, 256);
+        if (wt == 0) s_scale[rb] = make_float2(tm.scale, tm.tile_k);
       }
     };
     constexpr int kScanU = (5180 + 255) / 256;  // float4 per worker thread for a whole tile: 21
 
-    uint32_t ks = 0;   // running k-step index of the current tile's first k-step
     uint32_t nt = 0;   // running count of non-silent tiles
     TileMeta cur, nxt;
-    fetch(0, cur);
-    if (cur.mode == kModeAsync || cur.mode == kModeAsyncHead) {  // first tile: nobody has scanned it yet
-      const float mxf = raw_absmax_slice(reinterpret_cast<const float*>(smem + kSmemRaw), wt, 256, 0, kScanU);
-      const uint32_t mx = __reduce_max_sync(0xffffffffu, __float_as_uint(mxf));
-      if (lane == 0) atomicMax(&s_tilemax[0], mx);
-    }
-    worker_bar();
-    finish_scale(0, cur);
-    worker_bar();
-    if (wt == 0) s_tilemax[0] = 0u;  // next accumulated during tile 1's MMA phase (for tile 2), after more barriers
-    while (cur.mode != kModeDone) {
+    // (Every piece of straight-line code below has ONE call site: the kernel is instruction-fetch sensitive -- the two
+    //  SMs of a TPC share an instruction cache, and code copies or a rarely used path running on one SM slow down both.)
+    bool have_cur = false;
+    uint32_t hv[4][8], lv[4][8];
+    for (;;) {
+      fetch(have_cur ? nt + 1 : 0u, nxt);
+      if (!have_cur) {  // tile 0: nobody has scanned it yet; its scale and window table are ours to make
+        cur = nxt;
+        have_cur = true;
+        if (is_tma_mode(cur.mode)) {
+          const float mxf = raw_absmax_slice(reinterpret_cast<const float*>(smem + kSmemRaw), wt, 256, 0, kScanU);
+          const uint32_t mx = __reduce_max_sync(0xffffffffu, __float_as_uint(mxf));
+          if (lane == 0) atomicMax(&s_tilemax[0], mx);
+        }
+        worker_bar();
+        finish_scale(0, cur);
+        worker_bar();
+        if (wt == 0) s_tilemax[0] = 0u;
+        bar_arrive_n(kBarWs0, kBarBoth);  // the prep workers may start on tile 0
+        if (cur.mode == kModeDone) break;
+        continue;
+      }
       const uint32_t rb = nt & 1u;
       const int t0 = cur.tile * kTileM;
-      const float tile_k = cur.tile_k;
+#ifdef WFE_TC_TRACE
+      if (wt == 0 && nt < 58 && (blockIdx.x == 0 || blockIdx.x == 77 || blockIdx.x == 147))
+        g_tc_tiles[blockIdx.x == 0 ? 0 : (blockIdx.x == 77 ? 1 : 2)][nt] = clock64();
+      if (wt == 0 && blockIdx.x < 160) {
+        if (nt == 1) g_tc_cta[blockIdx.x][2] = clock64();
+        g_tc_cta[blockIdx.x][1] = nt;
+        g_tc_cta[blockIdx.x][3] = clock64();
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        g_tc_cta[blockIdx.x][0] = smid;
+      }
+#endif
       if (wt == 0) TCT(0, nt, 3);
-      // the next tile is already in the other raw buffer (its TMA was issued one epilogue ago)
-      fetch(nt + 1, nxt);
-      const bool scan_next = nxt.mode == kModeAsync || nxt.mode == kModeAsyncHead;
-      const float* const raw_next = reinterpret_cast<const float*>(smem + kSmemRaw + (rb ^ 1u) * kRawBufBytes);
-      // ---- MMA phase: the quarter's two warps take alternate k-steps (running index parity == hh) ----
+      TCW(0);
+      // this tile's scaled window and log-domain constant come from the prep workers (tile 0: from ourselves, above)
+      if (nt > 0) mbar_wait(&bar_ws, (nt - 1u) & 1u, err_flag);
+      const float tile_k = s_scale[rb].y;
+      // (the next tile is already in the other raw buffer: its TMA was issued one epilogue ago; edge tiles were staged above)
+      const float* const xrow = reinterpret_cast<const float*>(smem + kSmemRaw + rb * kRawBufBytes) + m * kRawPitch;
+      const float* const ws = ws_sm + rb * kWsFloats;
+      const uint32_t par = nt & 1u;
+      mbar_arrive(&bar_staged);  // the prep workers may look at the next tile (an edge tile has been staged above)
+      // ---- MMA phase.  Static k-step assignment per lane quarter: the prep worker takes k0, k1 (prepared while we were
+      //      in the previous epilogue) and k4; the half-1 worker, which leaves the epilogue first, k2 and k5; the half-0
+      //      worker k3 and k6.  Every warp has three tensor-core k-steps of time per k-step of its own. ----
 #pragma unroll 1
-      for (int j = (int)((ks & 1u) ^ (uint32_t)hh); j < kKSteps; j += 2) {
-        prep_kstep(rb, j, ks + (uint32_t)j);
-        if (lane == 0 && qt == 0) TCT(0, nt, 4 + j);
+      for (int r = 0; r < 2; ++r) {
+        const int j = 3 - hh + 3 * r;
+        prep_kstep_regs(xrow, ws, j, hv, lv);
+        if (r == 1) mbar_arrive(&bar_raw_empty[rb]);  // this thread is done reading the raw tile
+        TCW(1 + 2 * r);
+        deposit_kstep(bar_a_empty[j - 1], par, bar_a_full, a_slot0, hv, lv, err_flag);
+        TCW(2 + 2 * r);
       }
-      mbar_arrive(&bar_raw_empty[rb]);  // this thread is done reading the raw tile
-      // ---- maximum of the NEXT tile, in the shadow of the tensor core's last k-steps (interleaving it with the k-step
-      //      loop slowed the loop down by as much as it saved) ----
-      if (scan_next) {
-        const float mx_next = raw_absmax_slice(raw_next, wt, 256, 0, kScanU);
-        const uint32_t mx = __reduce_max_sync(0xffffffffu, __float_as_uint(mx_next));
-        if (lane == 0) atomicMax(&s_tilemax[rb ^ 1u], mx);
-      }
-      worker_bar();  // every warp's share of the next tile's maximum is in
-      finish_scale(rb ^ 1u, nxt);
 
       // ---- epilogue phase ----
       const bool valid = t0 + m < kNFrames;
@@ -739,6 +829,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_wait(&bar_d_full, nt & 1u, err_flag);
       tc_fence_after();
       if (wt == 0) TCT(1, nt, 1);
+      TCW(6);
       uint32_t rmax = 0u, rmin = 0x7f800000u;
       uint32_t qb0_[4][8], qb1_[4][8];  // two register buffers of TMEM columns: [n1][2 pairs x (re, re, im, im)]
       f2 P0, P1, P2, P3;
@@ -830,19 +921,72 @@ __global__ void __launch_bounds__(kThreads, 1)
         __threadfence_block();
         mbar_arrive(&bar_st_full[nt & 1u]);  // release: the tile's global stores (ordered by __syncwarp) and s_red
       }
-      worker_bar();  // the next tile's window table is complete (and everybody has read its maximum)
-      if (wt == 0) s_tilemax[rb ^ 1u] = 0u;  // next written two tiles from now, after another worker_bar
+      TCW(7);
       cur = nxt;
-      ks += kKSteps;
+      ++nt;
+      if (cur.mode == kModeDone) break;
+    }
+  } else if (warp < 12) {
+    // ======================================== PREP WORKERS ========================================
+    // One warp per lane quarter that only prepares operands: k-steps 0, 1 and 4 of every tile, k0 and k1 of the NEXT
+    // tile while the epilogue workers are busy with this one -- the tensor core restarts the moment the accumulators
+    // are drained.  They also turn the next tile's maximum into its scale and scaled window table.
+    reg_shrink<kRegsP>();
+    const int qt = warp - 8;
+    const int m = qt * 32 + lane;
+    const int pt = qt * 32 + lane;  // 0..127 among the prep workers
+    const uint32_t a_slot0 = tmem + ((uint32_t)(qt * 32) << 16) + kTmemA;
+    uint32_t hv[4][8], lv[4][8];
+    uint32_t nt = 0;
+    mbar_wait(&bar_meta_full[0], 0u, err_flag);
+    int mode = s_meta[0].mode;
+    if (mode != kModeDone) bar_sync_n(kBarWs0, kBarBoth);  // tile 0's window table is ready (later tiles: we made it)
+    while (mode != kModeDone) {
+      const uint32_t rb = nt & 1u, par = nt & 1u;
+      const float* const xrow = reinterpret_cast<const float*>(smem + kSmemRaw + rb * kRawBufBytes) + m * kRawPitch;
+      const float* const ws = ws_sm + rb * kWsFloats;
+      TCW(0);
+#pragma unroll 1
+      for (int jj = 0; jj < 3; ++jj) {
+        const int j = jj < 2 ? jj : 4;
+        prep_kstep_regs(xrow, ws, j, hv, lv);
+        if (jj == 2) mbar_arrive(&bar_raw_empty[rb]);  // k-steps 0, 1, 4: this thread is done reading the raw tile
+        TCW(1 + 2 * jj);
+        // k0 follows the previous tile's last MMAs (for tile 0: nothing -- parity 1 of a fresh barrier has "completed")
+        deposit_kstep(bar_a_empty[j == 0 ? kKSteps - 1 : j - 1], j == 0 ? par ^ 1u : par, bar_a_full, a_slot0, hv, lv, err_flag);
+        TCW(2 + 2 * jj);
+      }
+      // the next tile: geometry from the loader, maximum from the epilogue workers
+      mbar_wait(&bar_meta_full[rb ^ 1u], ((nt + 1u) >> 1) & 1u, err_flag);
+      mode = s_meta[rb ^ 1u].mode;
+      mbar_wait(&bar_staged, par, err_flag);
+      if (is_tma_mode(mode)) {
+        // the tile's maximum -> power-of-two scale -> scaled window table (we have a tensor-core k-step or two to spare)
+        const uint32_t mx = __reduce_max_sync(
+            0xffffffffu, raw_absmax_rolled(reinterpret_cast<const float*>(smem + kSmemRaw + (rb ^ 1u) * kRawBufBytes), pt, 128));
+        if (lane == 0) atomicMax(&s_tilemax[rb ^ 1u], mx);
+        bar_sync_n(kBarPrep, 128);
+        float scale, tile_k;
+        scale_from_max(s_tilemax[rb ^ 1u], scale, tile_k);
+        write_ws(ws_sm + (rb ^ 1u) * kWsFloats, scale, pt, 128);
+        if (pt == 0) s_scale[rb ^ 1u] = make_float2(scale, tile_k);
+      }
+      bar_sync_n(kBarPrep, 128);  // the table is complete and everybody has read the maximum
+      if (pt == 0) s_tilemax[rb ^ 1u] = 0u;  // next accumulated two tiles from now
+      mbar_arrive(&bar_ws);
+      TCW(7);
       ++nt;
     }
-  } else if (warp == 8) {
+  } else if (warp == kWarpMma) {
+    reg_shrink<kRegsH>();
     // =========================================== MMA ISSUER ===========================================
     // The whole warp walks the loop (waits included); one elected lane issues the tensor-core instructions.
     // B descriptors differ only in the start address: add (byte offset >> 4) to the low word (addresses < 256 KB)
     const uint64_t b_desc0 = smem_desc(smem_u32(b_sm), kBChunkBytes, 128);
     uint32_t ks = 0, nt = 0;
-    for (uint32_t id = blockIdx.x; id < p.total_tiles; id += gridDim.x) {
+    for (uint32_t i = 0; i * gridDim.x < p.total_tiles; ++i) {
+      const uint32_t id = cta_tile(i);
+      if (id >= p.total_tiles) continue;
       const Tile t = tile_info(p, id);
       if (t.mode == kModeSilent) continue;
       if (lane == 0) TCT(2, nt, 0);
@@ -864,7 +1008,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             mma_f16_ts(d, ah, bh, kIdesc, acc);
             mma_f16_ts(d, ah, bl, kIdesc, 1u);
             mma_f16_ts(d, al, bh, kIdesc, 1u);
-            mma_commit(&bar_a_empty[ks & 1u][n1]);  // implies tcgen05.fence::before_thread_sync
+            mma_commit(&bar_a_empty[j][n1]);  // implies tcgen05.fence::before_thread_sync
           }
           __syncwarp();
         }
@@ -874,40 +1018,99 @@ __global__ void __launch_bounds__(kThreads, 1)
       __syncwarp();
       ++nt;
     }
-  } else if (warp == 9) {
+  } else if (warp == kWarpLoad) {
+    reg_shrink<kRegsH>();
     // =========================================== LOADER ===========================================
     // One TMA per tile into the free raw buffer, the reflect-pad patch of a clip's first tile, and the tile's geometry:
     // handed to the workers through bar_meta_full.  (Scanning the tile for its maximum here too was tried: one warp
     // needs 9 k cycles for it and slows the two workers of its sub-partition -- the workers do it in their idle slots.)
+    // one past the last PCM element of the batch: a box that ends below it reads the caller's buffer, whatever clip it is in
+    int64_t extent = 0;
+    {
+      const int n_clips = (int)(p.total_tiles / (uint32_t)kNTiles);
+      for (int b = lane; b < n_clips; b += 32) {
+        const int64_t off = __ldg(p.offsets + b);
+        const int64_t avail = p.lengths != nullptr ? __ldg(p.lengths + b) : __ldg(p.offsets + b + 1) - off;
+        extent = max(extent, off + avail);
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) extent = max(extent, __shfl_xor_sync(0xffffffffu, extent, d));
+    }
     uint32_t nt = 0;
-    for (uint32_t id = blockIdx.x;; id += gridDim.x) {
+    uint32_t tma_loads[2] = {0u, 0u};
+    for (uint32_t i = 0;; ++i) {
       Tile t;
       t.mode = kModeDone;
       t.b = t.tile = t.len = 0;
       t.off = 0;
-      if (id < p.total_tiles) {
-        t = tile_info(p, id);
+      if (i * gridDim.x < p.total_tiles) {
+        const uint32_t id = cta_tile(i);
+        if (id >= p.total_tiles) continue;
+        t = tile_info(p, id, extent);
         if (t.mode == kModeSilent) continue;
       }
       const uint32_t rb = nt & 1u;
       float* const raw = reinterpret_cast<float*>(smem + kSmemRaw + rb * kRawBufBytes);
       if (lane == 0) TCT(3, nt, 0);
-      mbar_wait(&bar_raw_empty[rb], ((nt >> 1) & 1u) ^ 1u, err_flag);  // the workers have finished with this buffer's previous tile
+      mbar_wait<WFE_TC_SLEEP_LONG>(&bar_raw_empty[rb], ((nt >> 1) & 1u) ^ 1u, err_flag);  // the workers have finished with this buffer's previous tile
       if (lane == 0) TCT(3, nt, 1);
       float scale = 1.f, tile_k = 1.f;
-      if (t.mode == kModeAsync || t.mode == kModeAsyncHead) {
+      if (is_tma_mode(t.mode)) {
         if (elect_one()) {
           mbar_arrive_expect_tx(&bar_raw_full[rb], kRawBoxBytes);
           tma_load_2d(raw, &tmap, (int32_t)(t.off + (int64_t)(t.tile * kTileM * kHop - kNFft / 2)), 0, &bar_raw_full[rb]);
         }
         __syncwarp();
-        mbar_wait(&bar_raw_full[rb], (nt >> 1) & 1u, err_flag);
+        // (the phase of bar_raw_full[rb] counts the TMA loads into this buffer, not its uses: staged tiles never touch it.
+        //  Round-2 versions up to v16 took the parity from the use count and, after the first staged tile, stopped
+        //  waiting for the data -- a rare run-to-run difference at full size was the symptom.)
+        mbar_wait<WFE_TC_SLEEP_LONG>(&bar_raw_full[rb], tma_loads[rb] & 1u, err_flag);
+        ++tma_loads[rb];
         if (lane == 0) TCT(3, nt, 2);
         if (t.mode == kModeAsyncHead) {
           // first tile of a clip: the TMA started 200 samples before the clip; replace them by the centred reflect pad
-          for (int i = lane; i < kNFft / 2; i += 32) {
-            const int s = kNFft / 2 - i;  // raw[i] = x[200 - i]
-            raw[i + (i >= kHop ? kRawPitch - kHop : 0)] = s < t.len ? load_pcm(p.pcm, p.pcm_dtype, t.off + s, p.pcm_scale) : 0.f;
+          float v[7];
+#pragma unroll
+          for (int u = 0; u < 7; ++u) {
+            const int i = lane + 32 * u, s = kNFft / 2 - i;  // raw[i] = x[200 - i]
+            v[u] = (i < kNFft / 2 && s < t.len) ? load_pcm(p.pcm, p.pcm_dtype, t.off + s, p.pcm_scale) : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 7; ++u) {
+            const int i = lane + 32 * u;
+            if (i < kNFft / 2) raw[i + (i >= kHop ? kRawPitch - kHop : 0)] = v[u];
+          }
+          __syncwarp();
+        }
+        if (t.mode == kModeAsyncTail) {
+          // the clip ends inside this tile: everything from its end on is zero padding, or -- beyond sample 480000 -- the
+          // centred reflect pad; rows that no valid frame reads are zeroed too (the maximum is taken over the whole tile)
+          const int s_begin = t.tile * kTileM * kHop - kNFft / 2;
+          const int i0 = t.len - s_begin;  // first raw index past the clip (> 0: the tile is not silent)
+          // stores only (nothing here waits for memory): the rest of the clip's last row, then whole rows, 16 bytes at a time
+          const int r0 = i0 / kHop, c0 = i0 - r0 * kHop;
+          for (int c = c0 + lane; c < kHop; c += 32) raw[r0 * kRawPitch + c] = 0.f;
+          for (int q = lane; q < (kRawRows - 1 - r0) * (kHop / 4); q += 32) {
+            const int r = r0 + 1 + q / (kHop / 4);
+            *reinterpret_cast<float4*>(raw + r * kRawPitch + 4 * (q % (kHop / 4))) = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          __syncwarp();
+          // reflect pad: raw index i <-> sample s = s_begin + i >= 480000 <-> source 2 * 479999 - s (at most 200 of them, and
+          // only when the clip is (nearly) full length); all loads first, then all stores
+          const int ir = kNSamples - s_begin;  // raw index of sample 480000
+          float v[7];
+#pragma unroll
+          for (int u = 0; u < 7; ++u) {
+            const int sk = (kNSamples - 2) - (lane + 32 * u);  // source of raw index ir + lane + 32 u
+            v[u] = (lane + 32 * u < kNFft / 2 && sk >= 0 && sk < t.len) ? load_pcm(p.pcm, p.pcm_dtype, t.off + sk, p.pcm_scale) : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 7; ++u) {
+            const int i = ir + lane + 32 * u;
+            if (lane + 32 * u < kNFft / 2 && i < kRawRows * kHop) {
+              const int r = i / kHop;
+              raw[r * kRawPitch + (i - r * kHop)] = v[u];
+            }
           }
           __syncwarp();
         }
@@ -932,81 +1135,57 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (t.mode == kModeDone) break;
       ++nt;
     }
-  } else {
-    // =========================================== CLAMP BOOKS (warp 10) ===========================================
-    OutT* const out = reinterpret_cast<OutT*>(p.out);
-    int ring_head = 0, ring_count = 0;
+  } else if (warp == kWarpClamp) {
+    reg_shrink<kRegsH>();
+    // =========================================== CLAMP BOOKS ===========================================
+    // Publishes every tile's extrema for the clamp pass (clamp_kernel) and writes the attention mask of padding tiles.
     uint32_t nt = 0;
-    for (uint32_t id = blockIdx.x; id < p.total_tiles; id += gridDim.x) {
+    for (uint32_t i = 0; i * gridDim.x < p.total_tiles; ++i) {
+      const uint32_t id = cta_tile(i);
+      if (id >= p.total_tiles) continue;
       const Tile t = tile_info(p, id);
-      float mx, mn;
-      int silent = 0;
+      float mx;
+      uint32_t mnb;
       if (t.mode == kModeSilent) {
-        silent = 1;
-        mx = -1.5f;
-        mn = -__int_as_float(0x7f800000);
+        mx = -1.5f;  // (log10(1e-10) + 4) / 4: what the reference computes for zero padding
+        mnb = kMinSilent;
         if (p.mask != nullptr) {
           const int t0 = t.tile * kTileM;
           for (int f = lane; f < kTileM && t0 + f < kNFrames; f += 32) p.mask[(size_t)t.b * kNFrames + t0 + f] = 0;
         }
       } else {
-        mbar_wait(&bar_st_full[nt & 1u], (nt >> 1) & 1u, err_flag);
+        mbar_wait<WFE_TC_SLEEP_LONG>(&bar_st_full[nt & 1u], (nt >> 1) & 1u, err_flag);
         // a worker warp whose 32 frames lie beyond frame 3000 reports the identities (lg2(0) = -inf, lg2(inf) = +inf)
         mx = -__int_as_float(0x7f800000);
-        mn = __int_as_float(0x7f800000);
+        float mn = __int_as_float(0x7f800000);
 #pragma unroll
         for (int w = 0; w < 8; ++w) {
           mx = fmaxf(mx, s_red[nt & 1u][0][w]);
           mn = fminf(mn, s_red[nt & 1u][1][w]);
         }
+        mnb = __float_as_uint(mn);
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_st_empty[nt & 1u]);
         ++nt;
       }
-      // ring full (a clip whose other tiles lag far behind): resolve the oldest entry by waiting for its clip
-      if (ring_count == kRing) {
-        const int2 bt = s_pend_bt[ring_head];
-        const float2 pm = s_pend_mm[ring_head];
-        ring_head = (ring_head + 1) & (kRing - 1);
-        --ring_count;
-        const float fl = wait_clip_floor_tc(p.tile_key, bt.x, lane);
-        if (pm.x < fl) fix_tile_tc<OutT>(out, kNMel, bt.x, bt.y & ~kSilentBit, fl, (bt.y & kSilentBit) != 0 || pm.y <= fl, lane);
-      }
-      // publish this tile's maximum, remember the tile
       if (lane == 0) {
-        st_relaxed_u32(p.tile_key + (size_t)t.b * kNTiles + t.tile, f2key(mx));
-        const int slot = (ring_head + ring_count) & (kRing - 1);
-        s_pend_bt[slot] = make_int2(t.b, t.tile | (silent ? kSilentBit : 0));
-        s_pend_mm[slot] = make_float2(mn, mx);
+        p.tile_key[id] = f2key(mx);
+        p.tile_min[id] = mnb;
       }
-      __syncwarp();
-      ++ring_count;
-      // retire every pending tile whose clip is complete, oldest first (bounded: at most 3 per visit)
-      for (int tries = 0; tries < 3 && ring_count > 0; ++tries) {
-        const int2 bt = s_pend_bt[ring_head];
-        uint32_t k = lane < kNTiles ? ld_relaxed_u32(p.tile_key + (size_t)bt.x * kNTiles + lane) : 1u;
-        const bool zero = __any_sync(0xffffffffu, k == 0);
-        if (zero) break;
-        k = __reduce_max_sync(0xffffffffu, k);
-        const float fl = fmaxf(key2f(k) - 2.0f, -1.5f);
-        const float2 pm = s_pend_mm[ring_head];
-        ring_head = (ring_head + 1) & (kRing - 1);
-        --ring_count;
-        if (pm.x < fl) fix_tile_tc<OutT>(out, kNMel, bt.x, bt.y & ~kSilentBit, fl, (bt.y & kSilentBit) != 0 || pm.y <= fl, lane);
-      }
-    }
-    // drain: every remaining tile of these clips belongs to a running CTA whose clamp warp publishes without waiting
-    while (ring_count > 0) {
-      const int2 bt = s_pend_bt[ring_head];
-      const float2 pm = s_pend_mm[ring_head];
-      ring_head = (ring_head + 1) & (kRing - 1);
-      --ring_count;
-      const float fl = wait_clip_floor_tc(p.tile_key, bt.x, lane);
-      if (pm.x < fl) fix_tile_tc<OutT>(out, kNMel, bt.x, bt.y & ~kSilentBit, fl, (bt.y & kSilentBit) != 0 || pm.y <= fl, lane);
     }
   }
 
+  else {
+    reg_shrink<24>();  // sixteenth warp: only there so that every scheduler starts with four warps' worth of registers
+  }
+
   // ---- teardown ----
+#ifdef WFE_TC_TRACE
+  if (lane == 0 && warp >= kWarpMma && warp <= kWarpClamp && (blockIdx.x == 0 || blockIdx.x == 77 || blockIdx.x == 147))
+    g_tc_tiles[blockIdx.x == 0 ? 0 : (blockIdx.x == 77 ? 1 : 2)][61 - (warp - kWarpMma)] = clock64();
+  if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 77 || blockIdx.x == 147))
+    g_tc_tiles[blockIdx.x == 0 ? 0 : (blockIdx.x == 77 ? 1 : 2)][62] = clock64();
+#endif
   tc_fence_before();
   __syncthreads();
 #ifdef WFE_TC_TRACE
@@ -1017,7 +1196,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     g_tc_trace[(4 + (blockIdx.x ? 5 : 0)) * kTrPts + 3] = gt;
   }
 #endif
-  if (warp == 9) tmem_dealloc(tmem, kTmemCols);
+  if (warp == kWarpLoad) tmem_dealloc(tmem, kTmemCols);
 }
 
 }  // namespace tc

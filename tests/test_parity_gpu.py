@@ -217,7 +217,7 @@ def test_raw_c_abi_with_plain_pointers(fe80):
                         scratch.data_ptr(), C.c_void_p(st.cuda_stream))
     assert rc == 0, lib.wfe_last_error()
     st.synchronize()
-    assert lib.wfe_launch_count() == n0 + 1
+    assert lib.wfe_launch_count() in (n0 + 1, n0 + 2)  # tensor-core path: main kernel + clamp pass
     assert np.abs(out[0].cpu().numpy() - ologmel.logmel_clip(clip, 80, "fp64")).max() <= TOL
     assert int(mask.sum()) == 1875
     # errors come back as status + message, never as exceptions across the ABI
