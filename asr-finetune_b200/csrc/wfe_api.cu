@@ -2,11 +2,16 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <sched.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <memory>
 #include <mutex>
+#include <thread>
 #include <new>
 #include <string>
 #include <vector>
@@ -58,6 +63,96 @@ struct DeviceGuard {
 
 constexpr int kSlots = 3;
 
+// Host-side staging copies (pageable caller memory <-> the pinned ring) on a few persistent threads: one memcpy stream
+// moves ~8 GB/s, a PCIe 5 link 50+, so a single-threaded staging loop was what bound the drop-in call on the arrays the
+// reference's loader yields (one separately allocated pageable array per clip): 62 ms for 256 clips against 11 ms of PCIe.
+// (Non-temporal stores instead of memcpy were measured too: no gain, 15.5 vs 15.4 ms.)
+class CopyPool {
+ public:
+  struct Job {
+    char* dst;
+    const char* src;
+    size_t n;
+  };
+  explicit CopyPool(int n_threads) {
+    for (int i = 0; i < n_threads; ++i) workers_.emplace_back([this] { loop(); });
+  }
+  ~CopyPool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+      ++gen_;
+    }
+    cv_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+  // copies every job (cut into pieces of at most 256 KB); the calling thread takes part; returns when all are done
+  void run(const std::vector<Job>& jobs) {
+    pieces_.clear();
+    for (const Job& j : jobs)
+      for (size_t o = 0; o < j.n; o += kPiece) pieces_.push_back({j.dst + o, j.src + o, std::min(kPiece, j.n - o)});
+    if (pieces_.empty()) return;
+    if (workers_.empty() || pieces_.size() < 4) {
+      for (const Job& q : pieces_) memcpy(q.dst, q.src, q.n);
+      return;
+    }
+    next_.store(0, std::memory_order_relaxed);
+    left_.store(pieces_.size(), std::memory_order_relaxed);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      ++gen_;
+    }
+    cv_.notify_all();
+    work();
+    std::unique_lock<std::mutex> lk(mu_);
+    done_cv_.wait(lk, [this] { return left_.load(std::memory_order_acquire) == 0; });
+  }
+
+ private:
+  static constexpr size_t kPiece = 256 * 1024;
+  void work() {
+    for (;;) {
+      const size_t i = next_.fetch_add(1, std::memory_order_relaxed);
+      if (i >= pieces_.size()) return;
+      memcpy(pieces_[i].dst, pieces_[i].src, pieces_[i].n);
+      if (left_.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+        std::lock_guard<std::mutex> lk(mu_);
+        done_cv_.notify_all();
+      }
+    }
+  }
+  void loop() {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+      }
+      work();
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::vector<Job> pieces_;
+  std::atomic<size_t> next_{0}, left_{0};
+  std::mutex mu_;
+  std::condition_variable cv_, done_cv_;
+  uint64_t gen_ = 0;
+  bool stop_ = false;
+};
+
+int host_copy_threads() {
+  if (const char* e = getenv("WFE_HOST_THREADS")) {
+    const int v = atoi(e);
+    if (v >= 1) return std::min(v, 64);
+  }
+  int cores = (int)std::thread::hardware_concurrency();
+  cpu_set_t set;
+  if (sched_getaffinity(0, sizeof(set), &set) == 0) cores = CPU_COUNT(&set);
+  return std::max(1, std::min(8, cores / 2));
+}
+
 struct HostSlot {
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
@@ -96,6 +191,7 @@ struct wfe_handle {
   float4* d_mel_tab = nullptr;           // [n_rows][2 halves]
   wfe::MelGroup* d_mel_groups = nullptr; // [n_groups]
   std::mutex host_mu;
+  std::unique_ptr<CopyPool> pool;        // staging copies of wfe_extract_host (created with the ring)
   bool ring_ready = false;
   int chunk_clips = 16;
   HostSlot slots[kSlots];
@@ -314,6 +410,16 @@ int check_handle(const wfe_handle* h) {
   return WFE_OK;
 }
 
+// device memory of the handle's GPU (cudaMalloc / a torch CUDA tensor)?
+bool is_device_ptr(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice;
+}
+
 bool is_pinned_host(const void* p) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
@@ -363,6 +469,8 @@ int ensure_ring(wfe_handle* h) {
     WFE_CUDA(cudaMalloc(&s.d_scratch, scratch_bytes(h, (int)c)));
     WFE_CUDA(cudaMalloc((void**)&s.d_stats, c * 2 * sizeof(float)));
   }
+  if (!h->pool) h->pool.reset(new (std::nothrow) CopyPool(host_copy_threads() - 1));
+  if (!h->pool) return fail(WFE_ERR_NOMEM, "out of host memory");
   h->ring_ready = true;
   return WFE_OK;
 }
@@ -371,7 +479,7 @@ int ensure_ring(wfe_handle* h) {
 int retire_slot(wfe_handle* h, HostSlot& s) {
   if (!s.busy) return WFE_OK;
   WFE_CUDA(cudaEventSynchronize(s.done));
-  if (s.user_out) memcpy(s.user_out, s.h_out, s.pending_out_bytes);
+  if (s.user_out) h->pool->run({{static_cast<char*>(s.user_out), static_cast<const char*>(s.h_out), s.pending_out_bytes}});
   if (s.user_mask) memcpy(s.user_mask, s.h_mask, (size_t)s.pending_clips * h->n_frames * sizeof(int32_t));
   s.user_out = nullptr;
   s.user_mask = nullptr;
@@ -802,8 +910,14 @@ int wfe_extract_host_ex(wfe_handle* h, const void* const* clips, const int64_t* 
     }
   } ring_guard{h};
 
-  const bool out_pinned = is_pinned_host(out);
-  const bool mask_pinned = attn_mask != nullptr && is_pinned_host(attn_mask);
+  // `out` / `attn_mask` may also be DEVICE memory (the in-loop training consumer): the kernels then write
+  // straight into them and nothing comes back over PCIe
+  const bool out_device = is_device_ptr(out);
+  const bool mask_device = attn_mask != nullptr && is_device_ptr(attn_mask);
+  const bool out_pinned = !out_device && is_pinned_host(out);
+  const bool mask_pinned = attn_mask != nullptr && !mask_device && is_pinned_host(attn_mask);
+  if (out_device && ((reinterpret_cast<uintptr_t>(out) & 15u) != 0))
+    return fail(WFE_ERR_INVALID, "device `out` must be 16-byte aligned");
   const size_t clip_out = (size_t)h->cfg.n_mel * h->n_frames;
   uint64_t up = 0, down = 0;
   const int chunk = h->chunk_clips;
@@ -846,16 +960,20 @@ int wfe_extract_host_ex(wfe_handle* h, const void* const* clips, const int64_t* 
                                  cudaMemcpyHostToDevice, s.stream));
         i = j;
       } else {
-        // stage a maximal run of pageable clips, then one H2D for the run (alignment gaps travel too: < 32 B each)
+        // stage a maximal run of pageable clips (all copy threads), then one H2D for the run (alignment gaps travel too:
+        // < 32 B each)
         const int i0 = i;
         int last = i;
+        std::vector<CopyPool::Job> jobs;
         while (i < n && !(lens[i] > 0 && is_pinned_host(clips[c0 + i]))) {
           if (lens[i] > 0) {
-            memcpy(static_cast<char*>(s.h_in) + (size_t)starts[i] * es, clips[c0 + i], (size_t)lens[i] * es);
+            jobs.push_back({static_cast<char*>(s.h_in) + (size_t)starts[i] * es, static_cast<const char*>(clips[c0 + i]),
+                            (size_t)lens[i] * es});
             last = i;
           }
           ++i;
         }
+        h->pool->run(jobs);
         const size_t bytes = (size_t)(starts[last] + lens[last] - starts[i0]) * es;
         if (bytes)
           WFE_CUDA(cudaMemcpyAsync(static_cast<char*>(s.d_in) + (size_t)starts[i0] * es,
@@ -871,20 +989,23 @@ int wfe_extract_host_ex(wfe_handle* h, const void* const* clips, const int64_t* 
       if (rc != WFE_OK) return rc;
       stats = s.d_stats;
     }
-    rc = wfe_logmel_ex(h, s.d_in, pcm_dtype, pcm_scale, s.d_off, s.d_off + chunk, n, stats, s.d_out, out_dtype,
-                       attn_mask ? s.d_mask : nullptr, s.d_scratch, s.stream);
-    if (rc != WFE_OK) return rc;
     char* dst = static_cast<char*>(out) + (size_t)c0 * clip_out * os;
+    int32_t* mdst = attn_mask ? attn_mask + (size_t)c0 * h->n_frames : nullptr;
+    rc = wfe_logmel_ex(h, s.d_in, pcm_dtype, pcm_scale, s.d_off, s.d_off + chunk, n, stats, out_device ? dst : s.d_out,
+                       out_dtype, attn_mask ? (mask_device ? mdst : s.d_mask) : nullptr, s.d_scratch, s.stream);
+    if (rc != WFE_OK) return rc;
     s.pending_out_bytes = (size_t)n * clip_out * os;
-    if (out_pinned) {
+    if (out_device) {
+      // nothing to copy
+    } else if (out_pinned) {
       WFE_CUDA(cudaMemcpyAsync(dst, s.d_out, s.pending_out_bytes, cudaMemcpyDeviceToHost, s.stream));
+      down += (uint64_t)s.pending_out_bytes;
     } else {
       WFE_CUDA(cudaMemcpyAsync(s.h_out, s.d_out, s.pending_out_bytes, cudaMemcpyDeviceToHost, s.stream));
       s.user_out = dst;
+      down += (uint64_t)s.pending_out_bytes;
     }
-    down += (uint64_t)s.pending_out_bytes;
-    if (attn_mask) {
-      int32_t* mdst = attn_mask + (size_t)c0 * h->n_frames;
+    if (attn_mask && !mask_device) {
       if (mask_pinned) {
         WFE_CUDA(cudaMemcpyAsync(mdst, s.d_mask, (size_t)n * h->n_frames * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
       } else {

@@ -293,7 +293,7 @@ class WhisperFeatureExtractor:
         return bool(h.lib.wfe_uses_tensor_cores(h.ptr))
 
     def _extract_host(self, clips: Sequence[np.ndarray], n_samples: int, do_normalize: bool, want_mask: bool,
-                      out_dtype=None):
+                      out_dtype=None, to_device: bool = False):
         """Host numpy clips -> host (pinned) torch tensors through the pipelined C entry point.  The PCM crosses PCIe in
         its own width only when EVERY clip has that 2-byte dtype (int16 as-is, like HF; float16 widened exactly);
         mixed batches have already been converted to float32 by `__call__`."""
@@ -311,8 +311,12 @@ class WhisperFeatureExtractor:
         ptrs = (C.c_void_p * B)(*[c.ctypes.data for c in clips])
         lens = (C.c_int64 * B)(*[int(c.shape[0]) for c in clips])
         odt = _out_dtype(out_dtype)
-        out = torch.empty((B, h.n_mel, h.n_frames), dtype=odt, pin_memory=True)
-        mask = torch.empty((B, h.n_frames), dtype=torch.int32, pin_memory=True) if want_mask else None
+        if to_device:  # the in-loop training consumer: the kernels write straight into CUDA tensors, nothing comes back
+            out = torch.empty((B, h.n_mel, h.n_frames), dtype=odt, device=dev)
+            mask = torch.empty((B, h.n_frames), dtype=torch.int32, device=dev) if want_mask else None
+        else:
+            out = torch.empty((B, h.n_mel, h.n_frames), dtype=odt, pin_memory=True)
+            mask = torch.empty((B, h.n_frames), dtype=torch.int32, pin_memory=True) if want_mask else None
         up, down = C.c_uint64(0), C.c_uint64(0)
         _lib.check(h.lib.wfe_extract_host_ex(h.ptr, ptrs, lens, B, dt, 1.0, int(bool(do_normalize)), out.data_ptr(),
                                              _OUT_DTYPES[odt], mask.data_ptr() if mask is not None else None,
@@ -377,11 +381,14 @@ class WhisperFeatureExtractor:
                                                   pad_to_multiple_of)
         want_mask = bool(return_attention_mask if return_attention_mask is not None else self.return_attention_mask)
         norm = bool(do_normalize) if do_normalize is not None else bool(self.do_normalize)
-        if output_device is not None and str(output_device).startswith("cuda"):
-            return self._call_device_tensors([torch.from_numpy(c) for c in clips], truncation, pad_to_multiple_of,
-                                             return_tensors, return_attention_mask, padding, max_length, do_normalize,
-                                             output_device, output_dtype)
         clips = [c[:n] for c, n in zip(clips, lengths)]  # truncation (a no-op for clips that fit)
+        if output_device is not None and str(output_device).startswith("cuda"):
+            # host clips in, CUDA tensors out: the same pipelined upload (staging threads, three streams), no download
+            feats, mask = self._extract_host(clips, n_samples, norm, want_mask, output_dtype, to_device=True)
+            data = {"input_features": feats}
+            if want_mask:
+                data["attention_mask"] = mask
+            return BatchFeature(data)
         feats, mask = self._extract_host(clips, n_samples, norm, want_mask, output_dtype)
         if return_tensors in ("pt", "torch"):
             data = {"input_features": feats}

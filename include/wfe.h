@@ -159,11 +159,14 @@ int wfe_collate(wfe_handle* h, const int64_t* ids, const int64_t* offsets, int32
 /*
  * clips      HOST array of `batch` host pointers (pageable or pinned), dtype per pcm_dtype
  * lengths    HOST int64[batch], samples per clip
- * out        HOST float32 (batch, n_mel, n_frames); pinned memory avoids a staging copy
- * attn_mask  HOST int32 (batch, n_frames) or NULL
+ * out        HOST float32 (batch, n_mel, n_frames); pinned memory avoids a staging copy.  May also be DEVICE memory
+ *            of the handle's GPU (16-byte aligned): the kernels then write straight into it and nothing is
+ *            downloaded -- the in-loop training consumer (host clips in, CUDA tensors out)
+ * attn_mask  HOST (or DEVICE, like `out`) int32 (batch, n_frames) or NULL
  * do_normalize  0/1 (zero-mean unit-variance per clip before the STFT)
  * Work is cut into chunks of clips and pipelined: pinned staging -> H2D -> kernels -> D2H on the handle's
- * private streams.  Synchronous: returns when `out` is complete.  h2d_bytes/d2h_bytes (may be NULL) receive
+ * private streams; pageable clips are staged by a few persistent copy threads (WFE_HOST_THREADS, default
+ * min(8, cores / 2)).  Synchronous: returns when `out` is complete.  h2d_bytes/d2h_bytes (may be NULL) receive
  * the bytes that crossed PCIe.
  */
 int wfe_extract_host(wfe_handle* h, const void* const* clips, const int64_t* lengths, int32_t batch,
