@@ -809,11 +809,11 @@ __global__ void __launch_bounds__(kThreads, 1)
       const uint32_t par = nt & 1u;
       mbar_arrive(&bar_staged);  // the prep workers may look at the next tile (an edge tile has been staged above)
       // ---- MMA phase.  Static k-step assignment per lane quarter: the prep worker takes k0, k1 (prepared while we were
-      //      in the previous epilogue) and k4; the half-1 worker, which leaves the epilogue first, k2 and k5; the half-0
-      //      worker k3 and k6.  Every warp has three tensor-core k-steps of time per k-step of its own. ----
+      //      in the previous epilogue) and k2 (it is free the moment k1 is handed over; we are still finishing the
+      //      epilogue then); the half-1 worker, which leaves the epilogue first, k3 and k5; the half-0 worker k4 and k6. ----
 #pragma unroll 1
       for (int r = 0; r < 2; ++r) {
-        const int j = 3 - hh + 3 * r;
+        const int j = 4 - hh + 2 * r;
         prep_kstep_regs(xrow, ws, j, hv, lv);
         if (r == 1) mbar_arrive(&bar_raw_empty[rb]);  // this thread is done reading the raw tile
         TCW(1 + 2 * r);
@@ -928,7 +928,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else if (warp < 12) {
     // ======================================== PREP WORKERS ========================================
-    // One warp per lane quarter that only prepares operands: k-steps 0, 1 and 4 of every tile, k0 and k1 of the NEXT
+    // One warp per lane quarter that only prepares operands: k-steps 0, 1 and 2 of every tile, k0 and k1 of the NEXT
     // tile while the epilogue workers are busy with this one -- the tensor core restarts the moment the accumulators
     // are drained.  They also turn the next tile's maximum into its scale and scaled window table.
     reg_shrink<kRegsP>();
@@ -948,9 +948,9 @@ __global__ void __launch_bounds__(kThreads, 1)
       TCW(0);
 #pragma unroll 1
       for (int jj = 0; jj < 3; ++jj) {
-        const int j = jj < 2 ? jj : 4;
+        const int j = jj;
         prep_kstep_regs(xrow, ws, j, hv, lv);
-        if (jj == 2) mbar_arrive(&bar_raw_empty[rb]);  // k-steps 0, 1, 4: this thread is done reading the raw tile
+        if (jj == 2) mbar_arrive(&bar_raw_empty[rb]);  // k-steps 0, 1, 2: this thread is done reading the raw tile
         TCW(1 + 2 * jj);
         // k0 follows the previous tile's last MMAs (for tile 0: nothing -- parity 1 of a fresh barrier has "completed")
         deposit_kstep(bar_a_empty[j == 0 ? kKSteps - 1 : j - 1], j == 0 ? par ^ 1u : par, bar_a_full, a_slot0, hv, lv, err_flag);

@@ -78,6 +78,23 @@ def speechlike(seed: int, n: int = N_SAMPLES) -> np.ndarray:
     return out.astype(np.float32)
 
 
+def bursty(seed: int, n: int = N_SAMPLES, span_db: float = 60.0, amp: float = 0.1) -> np.ndarray:
+    """White noise under 0.2-s segments with gains spread over `span_db`: speech-like dynamics, so that the per-clip
+    clamp (max - 8) has elements to clamp in most 128-frame tiles (the data-dependent part of the kernel)."""
+    u = uniform_u32(seed, (n + 3199) // 3200, stream=19).astype(np.float64) / 4294967296.0
+    gain = np.repeat(10.0 ** (-(span_db / 20.0) * u), 3200)[:n]
+    return (noise(seed + 101, n, amp=1.0).astype(np.float64) * amp * gain).astype(np.float32)
+
+
+def click_in_silence(n: int = N_SAMPLES, at: float = 0.5) -> np.ndarray:
+    """A loud 5-sample click in near-silence (1e-4 noise): one tile holds the clip maximum, every other tile sits at or
+    below the clamp floor."""
+    x = 1e-4 * noise(23, n, amp=1.0).astype(np.float64)
+    c = int(n * at)
+    x[c:c + 5] += np.array([0.3, 0.9, -0.9, 0.6, -0.2])[:max(0, min(5, n - c))]
+    return x.astype(np.float32)
+
+
 def clip_lengths(seed: int, batch: int, lo: int = SR, hi: int = N_SAMPLES) -> np.ndarray:
     """L_i ~ U{lo..hi} (seed 1337 is the reference's random_seed)."""
     u = uniform_u32(seed, batch, stream=11).astype(np.uint64)

@@ -39,6 +39,10 @@ def golden_logmel_cases():
         cases.append((f"noise_len{n}_128", 128, lambda n=n: signals.noise(100 + n % 97, n)))
     cases.append(("tone_len112123_80", 80, lambda: signals.tone(440.0, 112123, 0.3)))
     cases.append(("speechlike_len250000_128", 128, lambda: signals.speechlike(9, 250000)))
+    cases.append(("bursty60_128", 128, lambda: signals.bursty(11)))
+    cases.append(("bursty60_80", 80, lambda: signals.bursty(12)))
+    cases.append(("bursty60_len300007_128", 128, lambda: signals.bursty(13, 300007)))
+    cases.append(("click_128", 128, lambda: signals.click_in_silence()))
     return cases
 
 

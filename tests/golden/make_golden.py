@@ -59,6 +59,11 @@ def logmel_cases():
         cases.append((f"noise_len{n}_128", 128, signals.noise(100 + n % 97, n)))
     cases.append(("tone_len112123_80", 80, signals.tone(440.0, 112123, 0.3)))
     cases.append(("speechlike_len250000_128", 128, signals.speechlike(9, 250000)))
+    # speech-like dynamics (the clamp has work in most tiles) and a loud click in near-silence
+    cases.append(("bursty60_128", 128, signals.bursty(11)))
+    cases.append(("bursty60_80", 80, signals.bursty(12)))
+    cases.append(("bursty60_len300007_128", 128, signals.bursty(13, 300007)))
+    cases.append(("click_128", 128, signals.click_in_silence()))
     return cases
 
 

@@ -18,6 +18,9 @@ from oracle import signals
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3  # north_star tolerance on (log10(mel)+4)/4 features
+# Regression bar next to the contract: the kernel's measured error is 1.2e-4 at worst on the golden set (split-precision
+# fp16 tensor-core DFT + lg2.approx); a change that costs accuracy must show up long before it reaches 1e-3.
+REGRESSION_TOL = 2e-4
 
 import asr_finetune_b200 as pkg  # noqa: E402
 
@@ -45,7 +48,8 @@ def test_reference_call_matches_golden(logmel_golden, fe128, fe80, key, n_mel, g
     assert pkg._lib.launch_count() > before, "no CUDA kernel ran"
     assert isinstance(out, np.ndarray) and out.shape == (n_mel, 3000) and out.dtype == np.float32
     check_against_golden(out, logmel_golden, key, "t", TOL)  # torch fp32 path = what the reference runs
-    check_against_golden(out, logmel_golden, key, "n", TOL)  # numpy fp64 path
+    err64 = check_against_golden(out, logmel_golden, key, "n", TOL)  # numpy fp64 path
+    assert err64 <= REGRESSION_TOL, f"{key}: {err64:.2e} is inside the 1e-3 contract but above the regression bar"
 
 
 def test_known_answers(fe128):
@@ -380,6 +384,12 @@ def test_in_loop_training_consumer_tiny_whisper(fe80):
     batch = coll({"audio": [signals.noise(i, 16000 * (i + 2)) for i in range(4)], "labels": signals.label_ids(3, 4, 5, 20)})
     moved = {k: v.to("cuda:0") for k, v in batch.items()}  # what data_collator_id does
     assert all(moved[k].data_ptr() == batch[k].data_ptr() for k in batch)  # no copy: already there
+    # the in-loop batch is the oracle's batch
+    clips = [signals.noise(i, 16000 * (i + 2)) for i in range(4)]
+    f_ref, l_ref = ocollate.collate_streaming([ologmel.logmel_clip(c, 80, "fp64") for c in clips],
+                                              signals.label_ids(3, 4, 5, 20), signals.EOT)
+    assert np.abs(batch["input_features"].cpu().numpy() - f_ref).max() <= REGRESSION_TOL
+    assert torch.equal(batch["labels"].cpu(), torch.from_numpy(l_ref))
     with torch.autocast("cuda", dtype=torch.float16):
         loss = model(input_features=batch["input_features"], labels=batch["labels"]).loss
     loss.backward()
@@ -482,3 +492,89 @@ def test_padding_variants_and_input_containers(fe80):
         padded, _ = ologmel.pad_or_truncate(c)
         refn = ologmel.logmel_clip(ologmel.zero_mean_unit_var(padded, len(c)), 80, "fp64")
         assert np.abs(on["input_features"][i] - refn).max() <= TOL
+
+
+def test_fused_half_precision_outputs_are_the_fp32_result_rounded_once(fe128, fe80):
+    # the autocast consumer (`fp16 = True`, ref:finetune/training/configs/largev3_debug.config:8) gets
+    # its features already rounded in the kernel's epilogue -- including the clamp pass over the 16-bit tensor
+    clips = [signals.bursty(3), signals.speechlike(4, 250000), signals.noise(5, 33333), signals.click_in_silence()]
+    for fe, n_mel in ((fe128, 128), (fe80, 80)):
+        f32 = fe(clips, sampling_rate=16000, return_tensors="pt", output_device="cuda")["input_features"]
+        for dt in (torch.float16, torch.bfloat16):
+            f16 = fe(clips, sampling_rate=16000, return_tensors="pt", output_device="cuda", output_dtype=dt)["input_features"]
+            assert f16.dtype == dt and torch.equal(f16, f32.to(dt)), (n_mel, dt)
+        host16 = fe(clips, sampling_rate=16000, return_tensors="pt", output_dtype=torch.float16)["input_features"]
+        assert host16.dtype == torch.float16 and not host16.is_cuda and torch.equal(host16, f32.to(torch.float16).cpu())
+        ref = ologmel.logmel_batch(clips, n_mel, "fp64")
+        assert np.abs(f32.cpu().numpy() - ref).max() <= REGRESSION_TOL
+
+
+def test_half_precision_pcm_ingest(fe128):
+    # fp16 PCM travels in its own width and is widened exactly on load
+    clips = [signals.noise(40 + i, int(n)).astype(np.float16) for i, n in enumerate((480000, 123457, 16000))]
+    got = fe128(clips, sampling_rate=16000, return_tensors="pt")["input_features"].numpy()
+    ref = ologmel.logmel_batch([c.astype(np.float32) for c in clips], 128, "fp64")
+    assert np.abs(got - ref).max() <= REGRESSION_TOL
+
+
+def test_host_clips_into_device_tensors_is_the_same_pipeline(fe128):
+    # the training path: pageable host clips in, CUDA tensors out (wfe_extract_host with device memory for `out`)
+    rng = np.random.default_rng(3)
+    clips = [np.array(signals.bursty(60 + i, int(n)), copy=True) for i, n in enumerate(rng.integers(8000, 480001, size=37))]
+    host = fe128(clips, sampling_rate=16000, return_tensors="pt", return_attention_mask=True)
+    up_host, down_host = fe128.last_transfer_bytes
+    devb = fe128(clips, sampling_rate=16000, return_tensors="pt", return_attention_mask=True, output_device="cuda")
+    up_dev, down_dev = fe128.last_transfer_bytes
+    assert devb["input_features"].is_cuda and devb["attention_mask"].is_cuda
+    assert torch.equal(devb["input_features"].cpu(), host["input_features"])
+    assert torch.equal(devb["attention_mask"].cpu(), host["attention_mask"])
+    assert up_dev == up_host and down_dev == 0 and down_host > 0  # nothing comes back over PCIe
+
+
+def test_clip_tails_by_tma_and_by_staging_agree_with_the_oracle(fe128):
+    # A tile that straddles the end of its clip is loaded by TMA and patched by the loader warp when the clip starts on a
+    # 16-byte boundary and something follows it in the buffer, and staged by the workers otherwise (odd start, last clip
+    # of the batch): both against the oracle, for lengths around tile and hop-row boundaries and for full-length clips
+    # (reflect pad at sample 480000).
+    lens = [480000, 479999, 479841, 470840 + 1, 470840, 20480, 20481, 20319, 163840 + 199, 163840 + 200, 163840 + 201,
+            300007, 480000, 77, 480000]
+    clips = [signals.bursty(200 + i, n) for i, n in enumerate(lens)]
+    dev = fe128.cuda_device()
+    ref = ologmel.logmel_batch(clips, 128, "fp64")
+    mref = ologmel.frame_attention_mask(lens)
+    for align in (8, 1):  # 8 samples = 32 bytes (TMA path), 1 sample = staged path
+        starts = np.zeros(len(lens), dtype=np.int64)
+        np.cumsum([(n + align - 1) // align * align + (0 if align == 8 else 1) for n in lens[:-1]], out=starts[1:])
+        pcm = torch.zeros(int(starts[-1] + lens[-1]), dtype=torch.float32, device=dev)
+        for c, o in zip(clips, starts):
+            pcm[o:o + len(c)] = torch.from_numpy(c).to(dev)
+        feats, mask = fe128.logmel_device(pcm, torch.from_numpy(starts).to(dev), len(lens), return_attention_mask=True,
+                                          lengths=torch.tensor(lens, dtype=torch.int64, device=dev))
+        assert fe128.debug_kernel_error() == 0
+        assert np.abs(feats.cpu().numpy() - ref).max() <= REGRESSION_TOL, align
+        assert np.array_equal(mask.cpu().numpy(), mref), align
+
+
+def test_speechlike_batch_1024_against_the_oracle_on_64_clips(fe128):
+    # BASELINE configs[2] size with the data-dependent path busy: 1024 ragged clips with speech-like dynamics (the clamp
+    # pass rewrites most tiles), 64 of them against the oracle, all of them by the device-side invariants
+    B = 1024
+    lens = signals.clip_lengths(77, B)
+    dev = fe128.cuda_device()
+    starts = np.zeros(B, dtype=np.int64)
+    np.cumsum((lens[:-1] + 7) & ~7, out=starts[1:])
+    g = torch.Generator(device=dev)
+    g.manual_seed(77)
+    total = int(starts[-1] + lens[-1])
+    seg = torch.rand((total + 3199) // 3200, device=dev, generator=g)
+    pcm = 0.1 * torch.randn(total, device=dev, generator=g) * torch.repeat_interleave(10.0 ** (-3.0 * seg), 3200)[:total]
+    feats, mask = fe128.logmel_device(pcm, torch.from_numpy(starts).to(dev), B, return_attention_mask=True,
+                                      lengths=torch.from_numpy(lens).to(dev))
+    feats2, _ = fe128.logmel_device(pcm, torch.from_numpy(starts).to(dev), B, lengths=torch.from_numpy(lens).to(dev))
+    assert torch.equal(feats, feats2)  # run-to-run identical
+    gmax = feats.amax(dim=(1, 2))
+    assert torch.isfinite(feats).all() and bool((feats.amin(dim=(1, 2)) >= gmax - 2.0).all())
+    assert torch.equal(mask.cpu(), torch.from_numpy(ologmel.frame_attention_mask(lens)))
+    for b in range(0, B, 16):
+        clip = pcm[starts[b]:starts[b] + lens[b]].cpu().numpy()
+        assert np.abs(feats[b].cpu().numpy() - ologmel.logmel_clip(clip, 128, "fp64")).max() <= REGRESSION_TOL, b

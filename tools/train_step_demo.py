@@ -9,6 +9,14 @@ forward -> backward -> AdamW on the adapters.  Compares the reference's CPU fron
 (`StreamingFrontendCollator`, CUDA tensors straight into the step).
 
     python tools/train_step_demo.py [--size large-v3|small|tiny] [--batch 8] [--steps 5]
+    torchrun --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tools/train_step_demo.py --ddp   # BASELINE configs[4]
+
+--ddp: one process per GPU (ref:finetune/training/train_hyper.py:319-329, N Ray workers), the model wrapped in
+DistributedDataParallel over NCCL (gradient all-reduce of the adapters: the only collective, and it is the trainer's, not
+the frontend's), every rank collating ITS OWN shard of clips (ref:finetune/training/trainers/trainers.py:785-791, 826-828)
+with `StreamingFrontendCollator(feature_dtype=float16)` as the collate_fn -- the fp16 cast fused into the kernel's
+epilogue.  Every rank checks its in-loop batch against the numpy oracle; rank 0 prints one JSON line with the max over
+ranks of the step times.
 """
 import argparse, json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -38,14 +46,21 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--size", default="large-v3"); ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--ddp", action="store_true")
     a = ap.parse_args()
+    rank, local_rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    if a.ddp:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank if a.ddp else 0)
     d = DIMS[a.size]
     cfg = tr.WhisperConfig(vocab_size=51866, num_mel_bins=d["n_mel"], d_model=d["d_model"], encoder_layers=d["layers"],
                            decoder_layers=d["layers"], encoder_attention_heads=d["heads"], decoder_attention_heads=d["heads"],
                            encoder_ffn_dim=d["ffn"], decoder_ffn_dim=d["ffn"], decoder_start_token_id=50258,
                            pad_token_id=50257, bos_token_id=50257, eos_token_id=50257)
     torch.manual_seed(0)
-    model = tr.WhisperForConditionalGeneration(cfg).to("cuda", dtype=torch.float16 if a.size == "large-v3" else torch.float32)
+    model = tr.WhisperForConditionalGeneration(cfg).to(dev, dtype=torch.float16 if a.size == "large-v3" else torch.float32)
     for p in model.parameters():
         p.requires_grad_(False)
     for m in list(model.modules()):
@@ -54,12 +69,16 @@ def main():
                 setattr(m, name, LoRALinear(getattr(m, name)))
     params = [p for p in model.parameters() if p.requires_grad]
     opt = torch.optim.AdamW(params, lr=1e-4)
-    rng = np.random.default_rng(0)
+    net = model
+    if a.ddp:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank])
+    rng = np.random.default_rng(1000 + rank)  # every rank draws its own shard of clips
     audio = [(0.1 * rng.standard_normal(int(rng.integers(16000, 480001)))).astype(np.float32) for _ in range(a.batch)]
     labels = [[50258, 50261, 50360, 50364] + rng.integers(0, 50257, int(rng.integers(5, 100))).tolist() + [50257]
               for _ in range(a.batch)]
-    ours = pkg.WhisperFeatureExtractor(feature_size=d["n_mel"])
-    gpu_collate = pkg.StreamingFrontendCollator(ours)
+    ours = pkg.WhisperFeatureExtractor(feature_size=d["n_mel"], cuda_device=dev.index)
+    # autocast consumer: features leave the kernel already in fp16 (ref:finetune/training/configs/largev3_debug.config:8)
+    gpu_collate = pkg.StreamingFrontendCollator(ours, feature_dtype=torch.float16 if a.ddp else None)
     ref_fe = tr.WhisperFeatureExtractor(feature_size=d["n_mel"])
 
     def cpu_collate(batch):  # the reference's loop + tokenizer.pad semantics + data_collator_id
@@ -68,14 +87,14 @@ def main():
         lab = torch.full((len(batch["labels"]), w), -100, dtype=torch.int64)
         for i, x in enumerate(batch["labels"]):
             lab[i, :len(x)] = torch.tensor(x)
-        return {"input_features": feats.to("cuda:0"), "labels": lab.to("cuda:0")}
+        return {"input_features": feats.to(dev), "labels": lab.to(dev)}
 
     def step(collate):
         t0 = time.perf_counter()
         b = collate({"audio": audio, "labels": labels})
         torch.cuda.synchronize(); t1 = time.perf_counter()
         with torch.autocast("cuda", dtype=torch.float16):
-            loss = model(input_features=b["input_features"].to(model.dtype), labels=b["labels"]).loss
+            loss = net(input_features=b["input_features"].to(model.dtype), labels=b["labels"]).loss
         loss.backward(); opt.step(); opt.zero_grad(set_to_none=True)
         torch.cuda.synchronize(); t2 = time.perf_counter()
         return (t1 - t0) * 1e3, (t2 - t1) * 1e3, float(loss)
@@ -87,11 +106,36 @@ def main():
         res[name] = {"collate_ms": float(np.median([t[0] for t in ts])), "model_ms": float(np.median([t[1] for t in ts])),
                      "loss": ts[-1][2]}
     fa = cpu_collate({"audio": audio, "labels": labels}); fb = gpu_collate({"audio": audio, "labels": labels})
-    res["frontends_agree"] = {"features_max_abs_err": float((fa["input_features"] - fb["input_features"]).abs().max()),
+    res["frontends_agree"] = {"features_max_abs_err": float((fa["input_features"] - fb["input_features"].float()).abs().max()),
                               "labels_equal": bool(torch.equal(fa["labels"], fb["labels"]))}
+    # the in-loop batch against the numpy oracle (test infrastructure; this tool is a measurement script, not product code)
+    from oracle import collate as ocollate, logmel as ologmel
+    ref = ologmel.logmel_batch(audio, d["n_mel"], "fp64")
+    got = fb["input_features"].float().cpu().numpy()
+    tol = 1e-3 + (2e-3 if fb["input_features"].dtype == torch.float16 else 0.0)  # + one fp16 rounding of values in [-1.5, 2]
+    res["oracle"] = {"features_max_abs_err": float(np.abs(got - ref).max()), "tolerance": tol,
+                     "labels_equal": bool(np.array_equal(fb["labels"].cpu().numpy(),
+                                                         ocollate.mask_labels(*ocollate.pad_label_ids(labels, 50257)))),
+                     "feature_dtype": str(fb["input_features"].dtype)}
+    assert res["oracle"]["features_max_abs_err"] <= tol and res["oracle"]["labels_equal"], res["oracle"]
     res["config"] = {"size": a.size, "batch": a.batch, "steps": a.steps, "lora_params": sum(p.numel() for p in params),
-                     "host_cores": len(os.sched_getaffinity(0)), "torch_threads": torch.get_num_threads()}
-    print(json.dumps(res))
+                     "host_cores": len(os.sched_getaffinity(0)), "torch_threads": torch.get_num_threads(),
+                     "world_size": world, "ddp": bool(a.ddp)}
+    if a.ddp:
+        # max over ranks of every timing; all ranks must have passed their oracle check to get here
+        keys = [(n, k) for n in ("cpu_frontend", "b200_frontend") for k in ("collate_ms", "model_ms")]
+        t = torch.tensor([res[n][k] for n, k in keys] + [res["oracle"]["features_max_abs_err"]], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        for (n, k), v in zip(keys, t.tolist()):
+            res[n][k] = v
+        res["oracle"]["features_max_abs_err_max_over_ranks"] = t.tolist()[-1]
+        res["global_batch"] = a.batch * world
+        dist.barrier()
+        if rank == 0:
+            print(json.dumps(res))
+        dist.destroy_process_group()
+    else:
+        print(json.dumps(res))
 
 
 if __name__ == "__main__":
