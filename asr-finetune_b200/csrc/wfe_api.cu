@@ -199,9 +199,15 @@ struct wfe_handle {
 
 namespace {
 
+// words of scratch per clip: the CUDA-core kernel keeps one key per 32-frame tile (zero = not published yet); the tensor-
+// core path one key per 128-frame tile + the minima of its kMinBlocks blocks.  Four more words follow the per-clip part:
+// tile counter, error word (+ pad to 16 B).
+size_t scratch_words_per_clip(const wfe_handle* h) {
+  const size_t tc_words = (size_t)wfe::tc::kNTiles * (1 + wfe::tc::kMinBlocks);
+  return (size_t)h->ntiles > tc_words ? (size_t)h->ntiles : tc_words;
+}
 size_t scratch_bytes(const wfe_handle* h, int batch) {
-  // tile_key[B][ntiles] (one word per tile, zero = not published yet), tile_counter, error word (+ pad to 16 B)
-  return ((size_t)batch * h->ntiles + 4) * sizeof(uint32_t);
+  return ((size_t)batch * scratch_words_per_clip(h) + 4) * sizeof(uint32_t);
 }
 
 template <typename T>
@@ -236,7 +242,7 @@ int launch_cc(wfe_handle* h, const void* pcm, float scale, const int64_t* offset
   p.out = out;
   p.mask = mask;
   p.tile_key = reinterpret_cast<uint32_t*>(scratch);
-  p.tile_counter = p.tile_key + (size_t)batch * h->ntiles;
+  p.tile_counter = p.tile_key + (size_t)batch * scratch_words_per_clip(h);
   p.s1_consts = h->d_s1_consts;
   p.mel_tab = h->d_mel_tab;
   p.mel_groups = h->d_mel_groups;
@@ -279,14 +285,14 @@ int launch_tc(wfe_handle* h, const void* pcm, int pcm_dtype, float scale, const 
   p.out = out;
   p.mask = mask;
   p.tile_key = reinterpret_cast<uint32_t*>(scratch);
-  p.tile_min = p.tile_key + (size_t)batch * wfe::tc::kNTiles;  // (the scratch is sized for the CUDA-core kernel's 94 tiles per clip)
+  p.tile_min = p.tile_key + (size_t)batch * wfe::tc::kNTiles;  // [B][24][kMinBlocks]
   p.b_mat = h->d_tc_b;
   p.tw = h->d_tc_tw;
   p.pcm_scale = scale;
   p.pcm_dtype = pcm_dtype;
   p.n_mel = kNMel;
   p.total_tiles = (uint32_t)total;
-  uint32_t* err_flag = p.tile_key + (size_t)batch * h->ntiles + 1;
+  uint32_t* err_flag = p.tile_key + (size_t)batch * scratch_words_per_clip(h) + 1;
   // 2-D view of the PCM for the raw-tile TMA: element (c, r) = pcm[c + 160 r]; a tile is the box (164 x 130) at
   // (first sample, 0): rows of 160 samples land on a 164-float pitch.  Only float32, 16-byte aligned PCM uses it; any
   // other input goes through the generic staging path and never touches the map (then it views a table of ours).
@@ -308,7 +314,7 @@ int launch_tc(wfe_handle* h, const void* pcm, int pcm_dtype, float scale, const 
   }
   if (!tma_ok && pcm_dtype == WFE_PCM_F32) p.pcm_dtype = 3;  // float32 at an odd address: generic staging only
   // (every tile word is written by the main kernel before the clamp pass reads it: only the error word needs clearing)
-  WFE_CUDA(cudaMemsetAsync(p.tile_key + (size_t)batch * h->ntiles, 0, 4 * sizeof(uint32_t), st));
+  WFE_CUDA(cudaMemsetAsync(p.tile_key + (size_t)batch * scratch_words_per_clip(h), 0, 4 * sizeof(uint32_t), st));
   long long grid = h->sm_count;
   if (grid > total) grid = total;
   wfe::tc::logmel_tc_kernel<OutT, kNMel><<<(unsigned)grid, wfe::tc::kThreads, wfe::tc::kSmemBytes, st>>>(p, tmap, err_flag);
@@ -790,7 +796,7 @@ int32_t wfe_debug_scratch_error(wfe_handle* h, const void* scratch, int32_t batc
   if (h == nullptr || scratch == nullptr || batch <= 0) return 0;
   DeviceGuard guard(h->cfg.device);
   uint32_t v = 0;
-  const uint32_t* w = reinterpret_cast<const uint32_t*>(scratch) + (size_t)batch * h->ntiles + 1;
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(scratch) + (size_t)batch * scratch_words_per_clip(h) + 1;
   if (cudaMemcpy(&v, w, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
   return (int32_t)v;
 }

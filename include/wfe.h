@@ -98,7 +98,7 @@ uint64_t wfe_launch_count(void);
 
 /* ---- log-mel features, device-resident input ---------------------------------------------------- */
 
-/* Bytes of device scratch wfe_logmel needs for `batch` clips (one max word per tile, tile scheduler counter, error word). */
+/* Bytes of device scratch wfe_logmel needs for `batch` clips (per-tile extrema for the per-clip clamp, tile scheduler counter, error word). */
 size_t wfe_logmel_scratch_bytes(const wfe_handle* h, int32_t batch);
 int32_t wfe_n_frames(const wfe_handle* h); /* n_samples / hop_length (3000) */
 
