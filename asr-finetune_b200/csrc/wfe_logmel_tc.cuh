@@ -107,6 +107,24 @@ constexpr size_t kSmemBytes = kSmemWs + 2 * kWsFloats * 4;           // 225760 (
 #undef WFE_TC_GEN_COUNTS
 constexpr int kMaxShared = kTcShared80 > kTcShared128 ? kTcShared80 : kTcShared128;  // filters fed by both epilogue halves
 
+#ifndef WFE_TC_STAGE_BATCH
+#define WFE_TC_STAGE_BATCH 2  // (8 in flight cost 1500 more SASS instructions and, although rarely run, 3 % of the kernel's speed)
+#endif
+#ifndef WFE_TC_L64
+#define WFE_TC_L64 0
+#endif
+#ifndef WFE_TC_ASSIGN
+#define WFE_TC_ASSIGN 0  // who prepares which k-step: 0 = P k0-k2, E k3..k6; 1 = P k0-k2 + k5, k6, E one each (k3 / k4)
+#endif
+#ifndef WFE_TC_P_THREE
+#define WFE_TC_P_THREE 0
+#endif
+#ifndef WFE_TC_E_BOTH
+#define WFE_TC_E_BOTH 0
+#endif
+#ifndef WFE_TC_SCAN_AFTER
+#define WFE_TC_SCAN_AFTER -1  // prep workers start on the next tile once this k-step's MMAs are done (-1: at once)
+#endif
 #ifndef WFE_TC_TRACE_CTA
 #define WFE_TC_TRACE_CTA 0
 #endif
@@ -205,26 +223,28 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
 #define WFE_TC_SLEEP_SHORT 32   // ns between probes of a latency-critical wait (operand slots, accumulators)
 #define WFE_TC_SLEEP_LONG 256   // ns between probes of a wait that is a tile long (raw buffers, clamp books)
 #endif
+// (One tight PTX loop per call site, ~8 SASS instructions: the kernel is instruction-fetch sensitive even to code it
+//  rarely runs, and the C++ version of this loop -- probe, sleep, count, report through an atomic -- came to ~20 per site
+//  at ~70 sites.)  `err_word` = shared-memory address of the CTA's time-out word, copied to global memory at the end.
 template <int kSleepNs = WFE_TC_SLEEP_SHORT>
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t* err_flag) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t spins = 0;
-  for (;;) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (ok) return;
-    // a probing warp takes issue slots from the warps that share its scheduler (measured: a bare probe loop costs the
-    // workers a third of theirs); a sleeping warp takes none
-    if (kSleepNs > 0) __nanosleep(kSleepNs);
-    if (++spins > (1u << 22)) break;
-  }
-  if (err_flag != nullptr) atomicExch(err_flag, 0xDEADu);
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t err_word) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .u32 n;\n\t"
+      "mov.u32 n, 0;\n"
+      "WFE_W:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WFE_D;\n\t"
+      "nanosleep.u32 %2;\n\t"  // a probing warp takes issue slots from the warps of its scheduler; a sleeping one none
+      "add.u32 n, n, 1;\n\t"
+      "setp.lt.u32 p, n, 4194304;\n\t"
+      "@p bra WFE_W;\n\t"
+      "st.shared.u32 [%3], 57005;\n"  // 0xDEAD: gave up
+      "WFE_D:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity), "n"(kSleepNs > 0 ? kSleepNs : 1), "r"(err_word)
+      : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -479,56 +499,30 @@ __device__ __forceinline__ void scale_from_max(uint32_t mx_bits, float& scale, f
   scale = __uint_as_float((uint32_t)(127 + 14 - e) << 23);
   tile_k = 1.0f - (float)(2 * (14 - e)) * (0.25f * kLog10_2);
 }
-// max |x| over a staged raw tile, as float bits, by `nthreads` cooperating threads (thread index t): thread t scans hop
-// rows t, t + nthreads, ... (row pitch 164 words: conflict-free LDS.128 across lanes), ten loads in flight
-__device__ __forceinline__ uint32_t raw_absmax(const float* raw, int t, int nthreads) {
+// max |x| over a raw tile, as float bits, by rows with 64-bit loads, nine in flight: warp `w4` of four takes hop rows w4, w4 + 4, ...; lanes read the
+// row's 80 float2 in three coalesced loads.  (tools/ubench_lds.cu: a conflict-free LDS.64 moves 256 B in 2 cycles, an
+// LDS.128 512 B in 8 -- per byte the 64-bit load costs the shared-memory pipe half as much.)
+__device__ __forceinline__ uint32_t raw_absmax_rows(const float* raw, int w4, int lane) {
+  constexpr int kPitch2 = kRawPitch / 2;  // 82 float2 per row
+  const float2* const p = reinterpret_cast<const float2*>(raw) + lane;
   float mx = 0.f;
-  for (int r = t; r < kRawRows; r += nthreads) {
-    const float4* row = reinterpret_cast<const float4*>(raw + r * kRawPitch);
-    const int n4 = r == kRawRows - 1 ? (kRawLen - (kRawRows - 1) * kHop) / 4 : kHop / 4;  // the last row is half a row
-#pragma unroll
-    for (int c0 = 0; c0 < kHop / 4; c0 += 10) {
-      float4 v[10];
-#pragma unroll
-      for (int u = 0; u < 10; ++u) v[u] = row[c0 + u];
-#pragma unroll
-      for (int u = 0; u < 10; ++u)
-        if (c0 + u < n4) mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v[u].x), fabsf(v[u].y)), fmaxf(fabsf(v[u].z), fabsf(v[u].w))));
-    }
-  }
-  return __float_as_uint(mx);
-}
-// the same for float4 elements i = t + nthreads * u, u in [u0, u1): slices that the workers fit between their k-steps
-__device__ __forceinline__ float raw_absmax_slice(const float* raw, int t, int nthreads, int u0, int u1) {
-  float mx = 0.f;
-  constexpr int kQuads = ((kRawRows - 1) * kHop + (kRawLen - (kRawRows - 1) * kHop)) / 4;  // 5180 float4 of real samples
-#pragma unroll
-  for (int u = u0; u < u1; ++u) {
-    const int i = t + nthreads * u;
-    if (i < kQuads) {
-      const int r = i / (kHop / 4);
-      const float4 v = *reinterpret_cast<const float4*>(raw + r * kRawPitch + 4 * (i - r * (kHop / 4)));
-      mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
-    }
-  }
-  return mx;
-}
-// the same as a compact loop over all 5180 float4 of a tile (four loads in flight)
-__device__ __forceinline__ uint32_t raw_absmax_rolled(const float* raw, int t, int nthreads) {
-  float mx = 0.f;
-  constexpr int kQuads = ((kRawRows - 1) * kHop + (kRawLen - (kRawRows - 1) * kHop)) / 4;
 #pragma unroll 1
-  for (int i0 = t; i0 < kQuads; i0 += 4 * nthreads) {
-    float4 v[4];
+  for (int r = w4; r < kRawRows - 1; r += 12) {
+    float2 v[9];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = min(i0 + u * nthreads, kQuads - 1);  // (re-reading the last element is harmless)
-      const int r = i / (kHop / 4);
-      v[u] = *reinterpret_cast<const float4*>(raw + r * kRawPitch + 4 * (i - r * (kHop / 4)));
+    for (int k = 0; k < 3; ++k) {
+      const float2* q = p + min(r + 4 * k, kRawRows - 2) * kPitch2;  // (re-reading a row is harmless)
+      v[3 * k] = q[0];
+      v[3 * k + 1] = q[32];
+      v[3 * k + 2] = lane < 16 ? q[64] : make_float2(0.f, 0.f);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v[u].x), fabsf(v[u].y)), fmaxf(fabsf(v[u].z), fabsf(v[u].w))));
+    for (int k = 0; k < 9; ++k) mx = fmaxf(mx, fmaxf(fabsf(v[k].x), fabsf(v[k].y)));
+  }
+  if (w4 == ((kRawRows - 1) & 3)) {  // the last row is half a row: 80 samples
+    const float2* q = p + (kRawRows - 1) * kPitch2;
+    const float2 a = q[0], b = lane < 8 ? q[32] : make_float2(0.f, 0.f);
+    mx = fmaxf(mx, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(b.x), fabsf(b.y))));
   }
   return __float_as_uint(mx);
 }
@@ -558,8 +552,20 @@ __device__ __forceinline__ void prep_kstep_regs(const float* xrow, const float* 
       float h[4][2], l[4][2];
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
+#if WFE_TC_L64
+        // 64-bit loads, conflict-free by frame because the lanes of every other group of eight start two floats in: the
+        // row pitch (164 words) alone puts lanes l and l + 8 on the same banks.  Those lanes see n1 ^ 2 in slot n1.
+        const int g2 = 2 * ((threadIdx.x >> 3) & 1);
+        const float2 xa = *reinterpret_cast<const float2*>(xp + 8 * q2 + 4 * q + g2);
+        const float2 xb = *reinterpret_cast<const float2*>(xp + 8 * q2 + 4 * q + 2 - g2);
+        const float2 wa = *reinterpret_cast<const float2*>(wp + 8 * q2 + 4 * q + g2);
+        const float2 wb = *reinterpret_cast<const float2*>(wp + 8 * q2 + 4 * q + 2 - g2);
+        const float4 x = make_float4(xa.x, xa.y, xb.x, xb.y);
+        const float4 w = make_float4(wa.x, wa.y, wb.x, wb.y);
+#else
         const float4 x = *reinterpret_cast<const float4*>(xp + 8 * q2 + 4 * q);
         const float4 w = *reinterpret_cast<const float4*>(wp + 8 * q2 + 4 * q);
+#endif
         // packed f32x2: the same roundings as four FMUL / FADD, half the issue slots
         const float2 y01 = __fmul2_rn(make_float2(x.x, x.y), make_float2(w.x, w.y));
         const float2 y23 = __fmul2_rn(make_float2(x.z, x.w), make_float2(w.z, w.w));
@@ -586,7 +592,7 @@ __device__ __forceinline__ void prep_kstep_regs(const float* xrow, const float* 
 // have read it: their commit arrives on `empty[n1]`, a barrier that completes exactly once per tile, so `parity` (the
 // tile's) is unambiguous whichever warp deposits.
 __device__ __forceinline__ void deposit_kstep(uint64_t* empty, uint32_t parity, uint64_t* full, uint32_t a_slot0,
-                                              const uint32_t (&hv)[4][8], const uint32_t (&lv)[4][8], uint32_t* err_flag) {
+                                              const uint32_t (&hv)[4][8], const uint32_t (&lv)[4][8], uint32_t err_flag) {
 #pragma unroll
   for (int n1 = 0; n1 < 4; ++n1) {
     mbar_wait(&empty[n1], parity, err_flag);
@@ -615,7 +621,7 @@ __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, 256;" :
 // ---------------------------------------------------------------------------------------------------------------
 template <typename OutT, int kNMel>
 __global__ void __launch_bounds__(kThreads, 1)
-    logmel_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap, uint32_t* err_flag) {
+    logmel_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap, uint32_t* err_global) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* const b_sm = smem + kSmemB;
   const float4* const tw_sm = reinterpret_cast<const float4*>(smem + kSmemTw);
@@ -625,6 +631,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       bar_d_empty, bar_st_full[2], bar_st_empty[2], bar_ws, bar_staged;
   __shared__ TileMeta s_meta[2];        // loader -> workers: geometry, scale and log-domain constant of the tile in buffer rb
   __shared__ uint32_t s_tmem;
+  __shared__ uint32_t s_err;            // set by a wait that gave up (mbar_wait); reported through err_global at the end
   __shared__ uint32_t s_pmax[8];        // generic staging: per-warp max |x| bits
   __shared__ uint32_t s_tilemax[2];     // per raw buffer: max |x| bits of the tile (atomicMax by the worker warps)
   __shared__ float2 s_scale[2];         // per raw buffer: (power-of-two scale, log-domain constant) of the tile
@@ -633,6 +640,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform: role branches do not diverge
+  const uint32_t err_flag = smem_u32(&s_err);
 #ifdef WFE_TC_TRACE
   if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 77 || blockIdx.x == 147))
     g_tc_tiles[blockIdx.x == 0 ? 0 : (blockIdx.x == 77 ? 1 : 2)][63] = clock64();
@@ -665,6 +673,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     mbar_init(&bar_d_full, 1);
     mbar_init(&bar_d_empty, 256);
     s_tilemax[0] = s_tilemax[1] = 0u;
+    s_err = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kWarpLoad) tmem_alloc(&s_tmem, kTmemCols);
@@ -703,7 +712,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       const bool vec_ok = (p.pcm_dtype == 0 || p.pcm_dtype == 3) &&
                           ((reinterpret_cast<uintptr_t>(reinterpret_cast<const float*>(p.pcm) + tm.off + s_begin) & 15u) == 0);
-      constexpr int kBatch = 8;  // quads of samples in flight per thread
+      constexpr int kBatch = WFE_TC_STAGE_BATCH;  // quads of samples in flight per thread
       for (int g0 = wt; g0 < n_quads; g0 += 256 * kBatch) {
         float4 v[kBatch];
 #pragma unroll
@@ -753,7 +762,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         *reinterpret_cast<float4*>(raw + r * kRawPitch + 4 * (g - r * (kHop / 4))) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       worker_bar();
-      uint32_t mx = __reduce_max_sync(0xffffffffu, raw_absmax(raw, wt, 256));
+      uint32_t mx = __reduce_max_sync(0xffffffffu, raw_absmax_rows(raw, warp & 3, lane));  // (both warps of a quarter scan the same rows: rare path, one code copy)
       if (lane == 0) s_pmax[warp] = mx;
       worker_bar();
       mx = max(max(max(s_pmax[0], s_pmax[1]), max(s_pmax[2], s_pmax[3])), max(max(s_pmax[4], s_pmax[5]), max(s_pmax[6], s_pmax[7])));
@@ -772,7 +781,6 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (wt == 0) s_scale[rb] = make_float2(tm.scale, tm.tile_k);
       }
     };
-    constexpr int kScanU = (5180 + 255) / 256;  // float4 per worker thread for a whole tile: 21
 
     uint32_t nt = 0;   // running count of non-silent tiles
     TileMeta cur, nxt;
@@ -786,8 +794,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         cur = nxt;
         have_cur = true;
         if (is_tma_mode(cur.mode)) {
-          const float mxf = raw_absmax_slice(reinterpret_cast<const float*>(smem + kSmemRaw), wt, 256, 0, kScanU);
-          const uint32_t mx = __reduce_max_sync(0xffffffffu, __float_as_uint(mxf));
+          const uint32_t mx = __reduce_max_sync(0xffffffffu, raw_absmax_rows(reinterpret_cast<const float*>(smem + kSmemRaw), warp & 3, lane));
           if (lane == 0) atomicMax(&s_tilemax[0], mx);
         }
         worker_bar();
@@ -825,6 +832,34 @@ __global__ void __launch_bounds__(kThreads, 1)
       // ---- MMA phase.  Static k-step assignment per lane quarter: the prep worker takes k0, k1 (prepared while we were
       //      in the previous epilogue) and k2 (it is free the moment k1 is handed over; we are still finishing the
       //      epilogue then); the half-1 worker, which leaves the epilogue first, k3 and k5; the half-0 worker k4 and k6. ----
+#if WFE_TC_E_BOTH
+      {
+        // both k-steps into registers first (the epilogue's 168 registers hold two operand sets), then the hand-overs at
+        // the tensor core's pace: the second k-step no longer starts only after the first has been taken
+        uint32_t hv2[4][8], lv2[4][8];
+        prep_kstep_regs(xrow, ws, 4 - hh, hv, lv);
+        TCW(1);
+        prep_kstep_regs(xrow, ws, 6 - hh, hv2, lv2);
+        mbar_arrive(&bar_raw_empty[rb]);  // this thread is done reading the raw tile
+        TCW(3);
+        deposit_kstep(bar_a_empty[3 - hh], par, bar_a_full, a_slot0, hv, lv, err_flag);
+        TCW(2);
+        deposit_kstep(bar_a_empty[5 - hh], par, bar_a_full, a_slot0, hv2, lv2, err_flag);
+        TCW(4);
+      }
+#elif WFE_TC_ASSIGN == 1
+      {
+        // one k-step per epilogue worker (half 1, which leaves the epilogue first: k3; half 0: k4): two preparations in a
+        // row by the same warp (1200-1800 cycles each while three warps per scheduler prepare) were the critical path of
+        // the MMA phase; the prep worker, idle between its hand-overs, takes k5 and k6
+        const int j = 4 - hh;
+        prep_kstep_regs(xrow, ws, j, hv, lv);
+        mbar_arrive(&bar_raw_empty[rb]);  // this thread is done reading the raw tile
+        TCW(1);
+        deposit_kstep(bar_a_empty[j - 1], par, bar_a_full, a_slot0, hv, lv, err_flag);
+        TCW(2);
+      }
+#else
 #pragma unroll 1
       for (int r = 0; r < 2; ++r) {
         const int j = 4 - hh + 2 * r;
@@ -834,6 +869,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         deposit_kstep(bar_a_empty[j - 1], par, bar_a_full, a_slot0, hv, lv, err_flag);
         TCW(2 + 2 * r);
       }
+#endif
 
       // ---- epilogue phase ----
       const bool valid = t0 + m < kNFrames;
@@ -948,7 +984,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     // One warp per lane quarter that only prepares operands: k-steps 0, 1 and 2 of every tile, k0 and k1 of the NEXT
     // tile while the epilogue workers are busy with this one -- the tensor core restarts the moment the accumulators
     // are drained.  They also turn the next tile's maximum into its scale and scaled window table.
-    reg_shrink<kRegsP>();
+    if constexpr (kRegsP > kRegsLaunch) reg_grow<kRegsP>(); else reg_shrink<kRegsP>();
     const int qt = warp - 8;
     const int m = qt * 32 + lane;
     const int pt = qt * 32 + lane;  // 0..127 among the prep workers
@@ -963,6 +999,39 @@ __global__ void __launch_bounds__(kThreads, 1)
       const float* const xrow = reinterpret_cast<const float*>(smem + kSmemRaw + rb * kRawBufBytes) + m * kRawPitch;
       const float* const ws = ws_sm + rb * kWsFloats;
       TCW(0);
+#if WFE_TC_P_THREE
+      // k0 goes to tensor memory as soon as the previous tile's last MMAs have read the slots; k1 AND k2 wait in registers
+      // (two operand sets: kRegsP = 176), so that all three are ready when the epilogue releases the accumulators -- with
+      // one set, k2 was prepared after k1 had been handed over and reached the tensor core ~1200 cycles late
+      {
+        uint32_t hv2[4][8], lv2[4][8];
+#pragma unroll 1
+        for (int jj = 0; jj < 2; ++jj) {
+          prep_kstep_regs(xrow, ws, jj, hv, lv);
+          TCW(1 + 2 * jj);
+          // k0 follows the previous tile's last MMAs (for tile 0: nothing -- parity 1 of a fresh barrier has "completed")
+          if (jj == 0) deposit_kstep(bar_a_empty[kKSteps - 1], par ^ 1u, bar_a_full, a_slot0, hv, lv, err_flag);
+        }
+        TCW(2);
+        prep_kstep_regs(xrow, ws, 2, hv2, lv2);
+        mbar_arrive(&bar_raw_empty[rb]);  // k-steps 0, 1, 2: this thread is done reading the raw tile
+        TCW(5);
+        deposit_kstep(bar_a_empty[0], par, bar_a_full, a_slot0, hv, lv, err_flag);
+        TCW(4);
+        deposit_kstep(bar_a_empty[1], par, bar_a_full, a_slot0, hv2, lv2, err_flag);
+        TCW(6);
+      }
+#elif WFE_TC_ASSIGN == 1
+#pragma unroll 1
+      for (int jj = 0; jj < 5; ++jj) {
+        const int j = jj < 3 ? jj : jj + 2;  // k0, k1, k2, k5, k6
+        prep_kstep_regs(xrow, ws, j, hv, lv);
+        if (jj == 4) mbar_arrive(&bar_raw_empty[rb]);  // this thread is done reading the raw tile
+        if (jj < 3) TCW(1 + 2 * jj);
+        deposit_kstep(bar_a_empty[j == 0 ? kKSteps - 1 : j - 1], j == 0 ? par ^ 1u : par, bar_a_full, a_slot0, hv, lv, err_flag);
+        if (jj < 3) TCW(2 + 2 * jj);
+      }
+#else
 #pragma unroll 1
       for (int jj = 0; jj < 3; ++jj) {
         const int j = jj;
@@ -973,6 +1042,14 @@ __global__ void __launch_bounds__(kThreads, 1)
         deposit_kstep(bar_a_empty[j == 0 ? kKSteps - 1 : j - 1], j == 0 ? par ^ 1u : par, bar_a_full, a_slot0, hv, lv, err_flag);
         TCW(2 + 2 * jj);
       }
+#endif
+#if WFE_TC_SCAN_AFTER >= 0
+      // Everything below works on the NEXT tile and has the whole epilogue phase of this one to finish in; started right
+      // away it would compete with the epilogue workers' k3..k6 for shared-memory bandwidth and issue slots, which is what
+      // paces the MMA phase (tools/ubench_lds.cu: an LDS.128 by frame occupies the pipe for 8 cycles; a tensor core at
+      // full rate takes half of the pipe for B).  So wait until the MMAs of k-step WFE_TC_SCAN_AFTER have been executed.
+      mbar_wait(&bar_a_empty[WFE_TC_SCAN_AFTER][3], par, err_flag);
+#endif
       // the next tile: geometry from the loader, maximum from the epilogue workers
       mbar_wait(&bar_meta_full[rb ^ 1u], ((nt + 1u) >> 1) & 1u, err_flag);
       mode = s_meta[rb ^ 1u].mode;
@@ -980,7 +1057,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (is_tma_mode(mode)) {
         // the tile's maximum -> power-of-two scale -> scaled window table (we have a tensor-core k-step or two to spare)
         const uint32_t mx = __reduce_max_sync(
-            0xffffffffu, raw_absmax_rolled(reinterpret_cast<const float*>(smem + kSmemRaw + (rb ^ 1u) * kRawBufBytes), pt, 128));
+            0xffffffffu, raw_absmax_rows(reinterpret_cast<const float*>(smem + kSmemRaw + (rb ^ 1u) * kRawBufBytes), qt, lane));
         if (lane == 0) atomicMax(&s_tilemax[rb ^ 1u], mx);
         bar_sync_n(kBarPrep, 128);
         float scale, tile_k;
@@ -1210,6 +1287,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
 #endif
   if (warp == kWarpLoad) tmem_dealloc(tmem, kTmemCols);
+  if (tid == 0 && s_err != 0u) atomicExch(err_global, 0xDEADu);
 }
 
 }  // namespace tc

@@ -32,5 +32,6 @@ for _ in range(iters):
     fe.logmel_device(pcm, offs, B, out=out, lengths=lengths)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / iters
+err = fe.debug_kernel_error()
 print(f"{os.environ.get('WFE_LIB_OVERRIDE','libwfe.so'):40s} B={B} n_mel={n_mel} {kind}: {ms:.4f} ms/launch  {audio_s/ms*1e3/1e6:.2f} M audio-s/s  "
-      f"{(audio_s*16000*4+B*n_mel*3000*4)/ms/1e6:.0f} GB/s  ({B/ms*1e3/1e6:.3f} M clips/s)")
+      f"{(audio_s*16000*4+B*n_mel*3000*4)/ms/1e6:.0f} GB/s  ({B/ms*1e3/1e6:.3f} M clips/s)" + (f"  KERNEL ERROR {err:#x}" if err else ""))
