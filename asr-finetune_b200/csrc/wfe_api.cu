@@ -286,6 +286,7 @@ int launch_tc(wfe_handle* h, const void* pcm, int pcm_dtype, float scale, const 
   p.mask = mask;
   p.tile_key = reinterpret_cast<uint32_t*>(scratch);
   p.tile_min = p.tile_key + (size_t)batch * wfe::tc::kNTiles;  // [B][24][kMinBlocks]
+  p.tile_counter = p.tile_key + (size_t)batch * scratch_words_per_clip(h);  // (cleared below, with the error word)
   p.b_mat = h->d_tc_b;
   p.tw = h->d_tc_tw;
   p.pcm_scale = scale;

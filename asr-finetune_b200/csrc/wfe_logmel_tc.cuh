@@ -110,21 +110,6 @@ constexpr int kMaxShared = kTcShared80 > kTcShared128 ? kTcShared80 : kTcShared1
 #ifndef WFE_TC_STAGE_BATCH
 #define WFE_TC_STAGE_BATCH 2  // (8 in flight cost 1500 more SASS instructions and, although rarely run, 3 % of the kernel's speed)
 #endif
-#ifndef WFE_TC_L64
-#define WFE_TC_L64 0
-#endif
-#ifndef WFE_TC_ASSIGN
-#define WFE_TC_ASSIGN 0  // who prepares which k-step: 0 = P k0-k2, E k3..k6; 1 = P k0-k2 + k5, k6, E one each (k3 / k4)
-#endif
-#ifndef WFE_TC_P_THREE
-#define WFE_TC_P_THREE 0
-#endif
-#ifndef WFE_TC_E_BOTH
-#define WFE_TC_E_BOTH 0
-#endif
-#ifndef WFE_TC_SCAN_AFTER
-#define WFE_TC_SCAN_AFTER -1  // prep workers start on the next tile once this k-step's MMAs are done (-1: at once)
-#endif
 #ifndef WFE_TC_TRACE_CTA
 #define WFE_TC_TRACE_CTA 0
 #endif
@@ -144,7 +129,15 @@ __device__ unsigned long long g_tc_cta[160][4];  // per CTA: smid, tiles done, f
   do {                                                                             \
     if (blockIdx.x == WFE_TC_TRACE_CTA && nt == 6 && lane == 0) g_tc_warps[warp][i] = clock64();  \
   } while (0)
+// start-up stamps of the traced CTA: row 12 = kernel, 13 = loader, 14 = epilogue warp 0, 15 = prep warp 8
+#define TCS(row, i)                                                                       \
+  do {                                                                                    \
+    if (blockIdx.x == WFE_TC_TRACE_CTA && (threadIdx.x & 31) == 0) g_tc_warps[row][i] = clock64(); \
+  } while (0)
 #else
+#define TCS(row, i) \
+  do {              \
+  } while (0)
 #define TCT(role, it, pt) \
   do {                    \
   } while (0)
@@ -161,6 +154,7 @@ struct TcParams {
   void* out;                // (B, n_mel, 3000), element type = template OutT
   int32_t* mask;
   uint32_t* tile_key;       // [B][24] key of each tile's maximum (f2key)
+  uint32_t* tile_counter;   // [1] dynamic tile scheduler (zero-initialised)
   uint32_t* tile_min;       // [B][24][16] float bits of the minimum of each (32 frames x 32 mels) block of a tile, or kMinSilent
   const uint4* b_mat;       // kBBytes: DFT-100 operand, canonical layout, hi then lo
   const float4* tw;         // kTwBytes: twiddles W400^(n1 k2)
@@ -378,7 +372,7 @@ __device__ __forceinline__ Tile tile_info(const TcParams& p, uint32_t id, int64_
     const int box_end = s_begin + (kRawRows - 1) * kHop + kRawPitch;
     if (base_ok && box_end <= t.len)
       t.mode = s_begin >= 0 ? kModeAsync : kModeAsyncHead;
-    else if (base_ok && s_begin >= 0 && t.off + box_end <= extent)
+    else if (base_ok && s_begin >= 0 && (extent < 0 || t.off + box_end <= extent))  // (extent < 0: the caller checks)
       // the tile that straddles the end of its clip: the box is still inside the caller's buffer (it reads into whatever
       // follows the clip), and the loader overwrites everything from the clip's end on (zeros / the reflect pad)
       t.mode = kModeAsyncTail;
@@ -387,11 +381,6 @@ __device__ __forceinline__ Tile tile_info(const TcParams& p, uint32_t id, int64_
   }
   return t;
 }
-
-// The CTA's i-th tile: row i of gridDim.x consecutive tile ids (clip-major: the CTAs work on the same few clips at any
-// time), column rotated by i, so that every CTA meets every tile-in-clip position -- clip heads and tails cost more than
-// interior tiles -- equally often.  A value >= total_tiles means "no tile in this (last, short) row".
-__device__ __forceinline__ uint32_t cta_tile(uint32_t i) { return i * gridDim.x + (blockIdx.x + i) % gridDim.x; }
 
 template <typename OutT>
 __device__ __forceinline__ OutT to_out(float v);
@@ -552,20 +541,8 @@ __device__ __forceinline__ void prep_kstep_regs(const float* xrow, const float* 
       float h[4][2], l[4][2];
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
-#if WFE_TC_L64
-        // 64-bit loads, conflict-free by frame because the lanes of every other group of eight start two floats in: the
-        // row pitch (164 words) alone puts lanes l and l + 8 on the same banks.  Those lanes see n1 ^ 2 in slot n1.
-        const int g2 = 2 * ((threadIdx.x >> 3) & 1);
-        const float2 xa = *reinterpret_cast<const float2*>(xp + 8 * q2 + 4 * q + g2);
-        const float2 xb = *reinterpret_cast<const float2*>(xp + 8 * q2 + 4 * q + 2 - g2);
-        const float2 wa = *reinterpret_cast<const float2*>(wp + 8 * q2 + 4 * q + g2);
-        const float2 wb = *reinterpret_cast<const float2*>(wp + 8 * q2 + 4 * q + 2 - g2);
-        const float4 x = make_float4(xa.x, xa.y, xb.x, xb.y);
-        const float4 w = make_float4(wa.x, wa.y, wb.x, wb.y);
-#else
         const float4 x = *reinterpret_cast<const float4*>(xp + 8 * q2 + 4 * q);
         const float4 w = *reinterpret_cast<const float4*>(wp + 8 * q2 + 4 * q);
-#endif
         // packed f32x2: the same roundings as four FMUL / FADD, half the issue slots
         const float2 y01 = __fmul2_rn(make_float2(x.x, x.y), make_float2(w.x, w.y));
         const float2 y23 = __fmul2_rn(make_float2(x.z, x.w), make_float2(w.z, w.w));
@@ -628,7 +605,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   float* const ws_sm = reinterpret_cast<float*>(smem + kSmemWs);  // [2 raw buffers][448]
 
   __shared__ uint64_t bar_raw_full[2], bar_raw_empty[2], bar_meta_full[2], bar_a_full[4], bar_a_empty[kKSteps][4], bar_d_full,
-      bar_d_empty, bar_st_full[2], bar_st_empty[2], bar_ws, bar_staged;
+      bar_d_empty, bar_st_full[2], bar_st_empty[2], bar_ws, bar_staged, bar_tab;
   __shared__ TileMeta s_meta[2];        // loader -> workers: geometry, scale and log-domain constant of the tile in buffer rb
   __shared__ uint32_t s_tmem;
   __shared__ uint32_t s_err;            // set by a wait that gave up (mbar_wait); reported through err_global at the end
@@ -653,9 +630,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 #endif
 
   // ---- one-time set-up ----
-  for (int i = tid; i < kBBytes / 16; i += kThreads) reinterpret_cast<uint4*>(b_sm)[i] = p.b_mat[i];
-  for (int i = tid; i < kTwBytes / 16; i += kThreads) reinterpret_cast<float4*>(smem + kSmemTw)[i] = p.tw[i];
-  fence_async_smem();  // B is read by the tensor core (async proxy)
+  if (tid == 0) TCS(12, 0);
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bar_raw_full[s], 1);
@@ -674,13 +649,21 @@ __global__ void __launch_bounds__(kThreads, 1)
     mbar_init(&bar_d_empty, 256);
     s_tilemax[0] = s_tilemax[1] = 0u;
     s_err = 0u;
+    mbar_init(&bar_tab, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // the constant tables (B operand 49 KB, twiddles) arrive by two bulk copies behind everything else of the start-up;
+    // their first users -- the MMA issuer, the epilogue -- wait for bar_tab.  (Copied by the threads, they cost the
+    // kernel ~5 k cycles before any role could start.)
+    mbar_arrive_expect_tx(&bar_tab, kBBytes + kTwBytes);
+    bulk_g2s(b_sm, p.b_mat, kBBytes, &bar_tab);
+    bulk_g2s(smem + kSmemTw, p.tw, kTwBytes, &bar_tab);
   }
   if (warp == kWarpLoad) tmem_alloc(&s_tmem, kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s_tmem;
+  if (tid == 0) TCS(12, 1);
 
   if (warp < 8) {
     // ====================================== EPILOGUE WORKERS ======================================
@@ -788,8 +771,10 @@ __global__ void __launch_bounds__(kThreads, 1)
     //  SMs of a TPC share an instruction cache, and code copies or a rarely used path running on one SM slow down both.)
     bool have_cur = false;
     uint32_t hv[4][8], lv[4][8];
+    mbar_wait<WFE_TC_SLEEP_LONG>(&bar_tab, 0u, err_flag);  // twiddles
     for (;;) {
       fetch(have_cur ? nt + 1 : 0u, nxt);
+      if (warp == 0 && nt == 0) TCS(14, have_cur ? 4 : 0);
       if (!have_cur) {  // tile 0: nobody has scanned it yet; its scale and window table are ours to make
         cur = nxt;
         have_cur = true;
@@ -798,8 +783,10 @@ __global__ void __launch_bounds__(kThreads, 1)
           if (lane == 0) atomicMax(&s_tilemax[0], mx);
         }
         worker_bar();
+        if (warp == 0) TCS(14, 1);
         finish_scale(0, cur);
         worker_bar();
+        if (warp == 0) TCS(14, 2);
         if (wt == 0) s_tilemax[0] = 0u;
         bar_arrive_n(kBarWs0, kBarBoth);  // the prep workers may start on tile 0
         if (cur.mode == kModeDone) break;
@@ -832,34 +819,6 @@ __global__ void __launch_bounds__(kThreads, 1)
       // ---- MMA phase.  Static k-step assignment per lane quarter: the prep worker takes k0, k1 (prepared while we were
       //      in the previous epilogue) and k2 (it is free the moment k1 is handed over; we are still finishing the
       //      epilogue then); the half-1 worker, which leaves the epilogue first, k3 and k5; the half-0 worker k4 and k6. ----
-#if WFE_TC_E_BOTH
-      {
-        // both k-steps into registers first (the epilogue's 168 registers hold two operand sets), then the hand-overs at
-        // the tensor core's pace: the second k-step no longer starts only after the first has been taken
-        uint32_t hv2[4][8], lv2[4][8];
-        prep_kstep_regs(xrow, ws, 4 - hh, hv, lv);
-        TCW(1);
-        prep_kstep_regs(xrow, ws, 6 - hh, hv2, lv2);
-        mbar_arrive(&bar_raw_empty[rb]);  // this thread is done reading the raw tile
-        TCW(3);
-        deposit_kstep(bar_a_empty[3 - hh], par, bar_a_full, a_slot0, hv, lv, err_flag);
-        TCW(2);
-        deposit_kstep(bar_a_empty[5 - hh], par, bar_a_full, a_slot0, hv2, lv2, err_flag);
-        TCW(4);
-      }
-#elif WFE_TC_ASSIGN == 1
-      {
-        // one k-step per epilogue worker (half 1, which leaves the epilogue first: k3; half 0: k4): two preparations in a
-        // row by the same warp (1200-1800 cycles each while three warps per scheduler prepare) were the critical path of
-        // the MMA phase; the prep worker, idle between its hand-overs, takes k5 and k6
-        const int j = 4 - hh;
-        prep_kstep_regs(xrow, ws, j, hv, lv);
-        mbar_arrive(&bar_raw_empty[rb]);  // this thread is done reading the raw tile
-        TCW(1);
-        deposit_kstep(bar_a_empty[j - 1], par, bar_a_full, a_slot0, hv, lv, err_flag);
-        TCW(2);
-      }
-#else
 #pragma unroll 1
       for (int r = 0; r < 2; ++r) {
         const int j = 4 - hh + 2 * r;
@@ -869,7 +828,6 @@ __global__ void __launch_bounds__(kThreads, 1)
         deposit_kstep(bar_a_empty[j - 1], par, bar_a_full, a_slot0, hv, lv, err_flag);
         TCW(2 + 2 * r);
       }
-#endif
 
       // ---- epilogue phase ----
       const bool valid = t0 + m < kNFrames;
@@ -878,6 +836,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (wt == 0) TCT(1, nt, 0);
       mbar_wait(&bar_d_full, nt & 1u, err_flag);
       tc_fence_after();
+      if (warp == 0 && nt == 0) TCS(14, 5);
       if (wt == 0) TCT(1, nt, 1);
       TCW(6);
       uint32_t rmax = 0u, rming[kMinGroups] = {0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u};
@@ -984,7 +943,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     // One warp per lane quarter that only prepares operands: k-steps 0, 1 and 2 of every tile, k0 and k1 of the NEXT
     // tile while the epilogue workers are busy with this one -- the tensor core restarts the moment the accumulators
     // are drained.  They also turn the next tile's maximum into its scale and scaled window table.
-    if constexpr (kRegsP > kRegsLaunch) reg_grow<kRegsP>(); else reg_shrink<kRegsP>();
+    reg_shrink<kRegsP>();
     const int qt = warp - 8;
     const int m = qt * 32 + lane;
     const int pt = qt * 32 + lane;  // 0..127 among the prep workers
@@ -993,45 +952,14 @@ __global__ void __launch_bounds__(kThreads, 1)
     uint32_t nt = 0;
     mbar_wait(&bar_meta_full[0], 0u, err_flag);
     int mode = s_meta[0].mode;
+    if (warp == 8) TCS(15, 0);
     if (mode != kModeDone) bar_sync_n(kBarWs0, kBarBoth);  // tile 0's window table is ready (later tiles: we made it)
+    if (warp == 8) TCS(15, 1);
     while (mode != kModeDone) {
       const uint32_t rb = nt & 1u, par = nt & 1u;
       const float* const xrow = reinterpret_cast<const float*>(smem + kSmemRaw + rb * kRawBufBytes) + m * kRawPitch;
       const float* const ws = ws_sm + rb * kWsFloats;
       TCW(0);
-#if WFE_TC_P_THREE
-      // k0 goes to tensor memory as soon as the previous tile's last MMAs have read the slots; k1 AND k2 wait in registers
-      // (two operand sets: kRegsP = 176), so that all three are ready when the epilogue releases the accumulators -- with
-      // one set, k2 was prepared after k1 had been handed over and reached the tensor core ~1200 cycles late
-      {
-        uint32_t hv2[4][8], lv2[4][8];
-#pragma unroll 1
-        for (int jj = 0; jj < 2; ++jj) {
-          prep_kstep_regs(xrow, ws, jj, hv, lv);
-          TCW(1 + 2 * jj);
-          // k0 follows the previous tile's last MMAs (for tile 0: nothing -- parity 1 of a fresh barrier has "completed")
-          if (jj == 0) deposit_kstep(bar_a_empty[kKSteps - 1], par ^ 1u, bar_a_full, a_slot0, hv, lv, err_flag);
-        }
-        TCW(2);
-        prep_kstep_regs(xrow, ws, 2, hv2, lv2);
-        mbar_arrive(&bar_raw_empty[rb]);  // k-steps 0, 1, 2: this thread is done reading the raw tile
-        TCW(5);
-        deposit_kstep(bar_a_empty[0], par, bar_a_full, a_slot0, hv, lv, err_flag);
-        TCW(4);
-        deposit_kstep(bar_a_empty[1], par, bar_a_full, a_slot0, hv2, lv2, err_flag);
-        TCW(6);
-      }
-#elif WFE_TC_ASSIGN == 1
-#pragma unroll 1
-      for (int jj = 0; jj < 5; ++jj) {
-        const int j = jj < 3 ? jj : jj + 2;  // k0, k1, k2, k5, k6
-        prep_kstep_regs(xrow, ws, j, hv, lv);
-        if (jj == 4) mbar_arrive(&bar_raw_empty[rb]);  // this thread is done reading the raw tile
-        if (jj < 3) TCW(1 + 2 * jj);
-        deposit_kstep(bar_a_empty[j == 0 ? kKSteps - 1 : j - 1], j == 0 ? par ^ 1u : par, bar_a_full, a_slot0, hv, lv, err_flag);
-        if (jj < 3) TCW(2 + 2 * jj);
-      }
-#else
 #pragma unroll 1
       for (int jj = 0; jj < 3; ++jj) {
         const int j = jj;
@@ -1042,14 +970,6 @@ __global__ void __launch_bounds__(kThreads, 1)
         deposit_kstep(bar_a_empty[j == 0 ? kKSteps - 1 : j - 1], j == 0 ? par ^ 1u : par, bar_a_full, a_slot0, hv, lv, err_flag);
         TCW(2 + 2 * jj);
       }
-#endif
-#if WFE_TC_SCAN_AFTER >= 0
-      // Everything below works on the NEXT tile and has the whole epilogue phase of this one to finish in; started right
-      // away it would compete with the epilogue workers' k3..k6 for shared-memory bandwidth and issue slots, which is what
-      // paces the MMA phase (tools/ubench_lds.cu: an LDS.128 by frame occupies the pipe for 8 cycles; a tensor core at
-      // full rate takes half of the pipe for B).  So wait until the MMAs of k-step WFE_TC_SCAN_AFTER have been executed.
-      mbar_wait(&bar_a_empty[WFE_TC_SCAN_AFTER][3], par, err_flag);
-#endif
       // the next tile: geometry from the loader, maximum from the epilogue workers
       mbar_wait(&bar_meta_full[rb ^ 1u], ((nt + 1u) >> 1) & 1u, err_flag);
       mode = s_meta[rb ^ 1u].mode;
@@ -1078,11 +998,10 @@ __global__ void __launch_bounds__(kThreads, 1)
     // B descriptors differ only in the start address: add (byte offset >> 4) to the low word (addresses < 256 KB)
     const uint64_t b_desc0 = smem_desc(smem_u32(b_sm), kBChunkBytes, 128);
     uint32_t ks = 0, nt = 0;
-    for (uint32_t i = 0; i * gridDim.x < p.total_tiles; ++i) {
-      const uint32_t id = cta_tile(i);
-      if (id >= p.total_tiles) continue;
-      const Tile t = tile_info(p, id);
-      if (t.mode == kModeSilent) continue;
+    mbar_wait<WFE_TC_SLEEP_LONG>(&bar_tab, 0u, err_flag);  // B
+    for (;;) {
+      mbar_wait<WFE_TC_SLEEP_LONG>(&bar_meta_full[nt & 1u], (nt >> 1) & 1u, err_flag);  // the loader has handed out another tile (or none)
+      if (s_meta[nt & 1u].mode == kModeDone) break;
       if (lane == 0) TCT(2, nt, 0);
       mbar_wait(&bar_d_empty, (nt & 1u) ^ 1u, err_flag);  // epilogue has drained the previous tile's accumulators
       tc_fence_after();
@@ -1119,17 +1038,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     // handed to the workers through bar_meta_full.  (Scanning the tile for its maximum here too was tried: one warp
     // needs 9 k cycles for it and slows the two workers of its sub-partition -- the workers do it in their idle slots.)
     // one past the last PCM element of the batch: a box that ends below it reads the caller's buffer, whatever clip it is in
-    int64_t extent = 0;
-    {
-      const int n_clips = (int)(p.total_tiles / (uint32_t)kNTiles);
-      for (int b = lane; b < n_clips; b += 32) {
-        const int64_t off = __ldg(p.offsets + b);
-        const int64_t avail = p.lengths != nullptr ? __ldg(p.lengths + b) : __ldg(p.offsets + b + 1) - off;
-        extent = max(extent, off + avail);
-      }
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) extent = max(extent, __shfl_xor_sync(0xffffffffu, extent, d));
-    }
+    int64_t extent = -1;  // computed when the first clip tail asks for it: at the start it would delay the first tile by 5 k cycles
+    TCS(13, 0);
     uint32_t nt = 0;
     uint32_t tma_loads[2] = {0u, 0u};
     for (uint32_t i = 0;; ++i) {
@@ -1137,14 +1047,54 @@ __global__ void __launch_bounds__(kThreads, 1)
       t.mode = kModeDone;
       t.b = t.tile = t.len = 0;
       t.off = 0;
-      if (i * gridDim.x < p.total_tiles) {
-        const uint32_t id = cta_tile(i);
-        if (id >= p.total_tiles) continue;
+      // Tiles are handed out in order from a global counter: the SMs do not run at the same pace (the first TPC of every
+      // GPC is ~12 % faster than the last ones -- instruction supply), and with a static split the slowest CTA sets the
+      // launch time.  The round trip of the atomic hides behind the wait for the raw buffer below.
+      uint32_t id = blockIdx.x;  // (the first tile without the atomic's round trip)
+      if (i > 0) {
+        if (lane == 0) id = atomicAdd(p.tile_counter, 1u) + gridDim.x;
+        id = __shfl_sync(0xffffffffu, id, 0);
+      }
+      if (id < p.total_tiles) {
         t = tile_info(p, id, extent);
-        if (t.mode == kModeSilent) continue;
+        if (t.mode == kModeAsyncTail) {
+          // the box reads past the clip: fine as long as it stays inside the caller's buffer, i.e. below the end of the
+          // last clip (known after one pass over the batch's offsets, made when the first tail shows up)
+          if (extent < 0) {
+            extent = 0;
+            // (eight clips per lane in flight: a rolled loop pays one global-memory latency per 32 clips -- 8 k cycles of the
+            //  kernel's start for a batch of 256)
+            const int n_clips = (int)(p.total_tiles / (uint32_t)kNTiles);
+            for (int b0 = lane; b0 < n_clips; b0 += 32 * 8) {
+              int64_t off[8], end[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const int b = min(b0 + 32 * u, n_clips - 1);  // (re-reading the last clip is harmless)
+                off[u] = __ldg(p.offsets + b);
+                end[u] = p.lengths != nullptr ? __ldg(p.lengths + b) : __ldg(p.offsets + b + 1);
+              }
+#pragma unroll
+              for (int u = 0; u < 8; ++u) extent = max(extent, p.lengths != nullptr ? off[u] + end[u] : end[u]);
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) extent = max(extent, __shfl_xor_sync(0xffffffffu, extent, d));
+          }
+          if (t.off + (int64_t)(t.tile * kTileM * kHop - kNFft / 2 + (kRawRows - 1) * kHop + kRawPitch) > extent) t.mode = kModeSync;
+        }
+        if (t.mode == kModeSilent) {
+          // a tile wholly in the zero padding is never computed: published for the clamp pass (which fills it) right here
+          if (lane == 0) p.tile_key[id] = f2key(-1.5f);  // (log10(1e-10) + 4) / 4: what the reference computes for zero padding
+          if (lane < kMinBlocks) p.tile_min[(size_t)id * kMinBlocks + lane] = kMinSilent;
+          if (p.mask != nullptr) {
+            const int t0 = t.tile * kTileM;
+            for (int f = lane; f < kTileM && t0 + f < kNFrames; f += 32) p.mask[(size_t)t.b * kNFrames + t0 + f] = 0;
+          }
+          continue;
+        }
       }
       const uint32_t rb = nt & 1u;
       float* const raw = reinterpret_cast<float*>(smem + kSmemRaw + rb * kRawBufBytes);
+      if (nt < 2) TCS(13, 1 + 3 * nt);
       if (lane == 0) TCT(3, nt, 0);
       mbar_wait<WFE_TC_SLEEP_LONG>(&bar_raw_empty[rb], ((nt >> 1) & 1u) ^ 1u, err_flag);  // the workers have finished with this buffer's previous tile
       if (lane == 0) TCT(3, nt, 1);
@@ -1159,6 +1109,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         //  Round-2 versions up to v16 took the parity from the use count and, after the first staged tile, stopped
         //  waiting for the data -- a rare run-to-run difference at full size was the symptom.)
         mbar_wait<WFE_TC_SLEEP_LONG>(&bar_raw_full[rb], tma_loads[rb] & 1u, err_flag);
+        if (nt < 2) TCS(13, 2 + 3 * nt);
         ++tma_loads[rb];
         if (lane == 0) TCT(3, nt, 2);
         if (t.mode == kModeAsyncHead) {
@@ -1167,7 +1118,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
           for (int u = 0; u < 7; ++u) {
             const int i = lane + 32 * u, s = kNFft / 2 - i;  // raw[i] = x[200 - i]
-            v[u] = (i < kNFft / 2 && s < t.len) ? load_pcm(p.pcm, p.pcm_dtype, t.off + s, p.pcm_scale) : 0.f;
+            v[u] = (i < kNFft / 2 && s < t.len) ? __ldg(reinterpret_cast<const float*>(p.pcm) + t.off + s) : 0.f;  // (TMA tiles are float32)
           }
 #pragma unroll
           for (int u = 0; u < 7; ++u) {
@@ -1196,7 +1147,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
           for (int u = 0; u < 7; ++u) {
             const int sk = (kNSamples - 2) - (lane + 32 * u);  // source of raw index ir + lane + 32 u
-            v[u] = (lane + 32 * u < kNFft / 2 && sk >= 0 && sk < t.len) ? load_pcm(p.pcm, p.pcm_dtype, t.off + sk, p.pcm_scale) : 0.f;
+            v[u] = (lane + 32 * u < kNFft / 2 && sk >= 0 && sk < t.len) ? __ldg(reinterpret_cast<const float*>(p.pcm) + t.off + sk) : 0.f;
           }
 #pragma unroll
           for (int u = 0; u < 7; ++u) {
@@ -1226,6 +1177,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         mbar_arrive(&bar_meta_full[rb]);
         TCT(3, nt, 3);
       }
+      if (nt < 2) TCS(13, 3 + 3 * nt);
       if (t.mode == kModeDone) break;
       ++nt;
     }
@@ -1234,10 +1186,15 @@ __global__ void __launch_bounds__(kThreads, 1)
     // =========================================== CLAMP BOOKS ===========================================
     // Publishes every tile's extrema for the clamp pass (clamp_kernel) and writes the attention mask of padding tiles.
     uint32_t nt = 0;
-    for (uint32_t i = 0; i * gridDim.x < p.total_tiles; ++i) {
-      const uint32_t id = cta_tile(i);
-      if (id >= p.total_tiles) continue;
-      const Tile t = tile_info(p, id);
+    for (;;) {
+      // (the tile's meta data stays in s_meta until the workers have finished reading its raw samples: long enough)
+      mbar_wait<WFE_TC_SLEEP_LONG>(&bar_meta_full[nt & 1u], (nt >> 1) & 1u, err_flag);
+      Tile t;
+      t.b = s_meta[nt & 1u].b;
+      t.tile = s_meta[nt & 1u].tile;
+      t.mode = s_meta[nt & 1u].mode;
+      if (t.mode == kModeDone) break;
+      const uint32_t id = (uint32_t)t.b * (uint32_t)kNTiles + (uint32_t)t.tile;
       float mx;
       uint32_t mnb;  // lanes 0..15: minimum of block (frame quarter lane / 4, mel group lane % 4)
       if (t.mode == kModeSilent) {

@@ -57,8 +57,13 @@ for r in rows:
 ww = np.zeros(128, dtype=np.uint64)
 assert lib.wfe_debug_read_tc_warps(ww.ctypes.data_as(C.c_void_p)) == 0
 ww = ww.reshape(16, 8).astype(np.int64)
-w0 = ww[ww > 0].min()
+w0 = ww[:12][ww[:12] > 0].min()
 print("per worker warp, traced CTA, tile iteration 6.  E half 0: [tile start, k2 ready, k2 deposited, scanned, k5 ready, k5 deposited, d_full ok, epilogue end]; E half 1: [start, scanned, k3 ready, k3 deposited, k6 ready, k6 deposited, d_full ok, epilogue end]; P: [start, k4 ready, k4 deposited, scan barrier passed, ws out, k0' ready, k0' deposited, k1' deposited]")
+k0 = int(ww[12, 0])
+print(f"start-up of the traced CTA (cycles after kernel entry): set-up done {int(ww[12,1])-k0}; "
+      f"loader [extent done, (tile 0: got tile, TMA landed, meta out), (tile 1: ...)] {[int(x)-k0 for x in ww[13,:7]]}; "
+      f"epilogue warp 0 [got tile 0, scanned, window table out, -, got tile 1, first accumulators ready] {[int(x)-k0 if x>0 else 0 for x in ww[14,:6]]}; "
+      f"prep warp 8 [got tile 0, may start] {[int(x)-k0 for x in ww[15,:2]]}")
 for w in range(12):
     print(f"   warp {w} (quarter {w % 4}, {'E half ' + str(w // 4) if w < 8 else 'P'}): {[int(x - w0) for x in ww[w]]}")
 kstart = int(tr[0, 4, 0])
