@@ -927,7 +927,17 @@ int wfe_extract_host_ex(wfe_handle* h, const void* const* clips, const int64_t* 
     return fail(WFE_ERR_INVALID, "device `out` must be 16-byte aligned");
   const size_t clip_out = (size_t)h->cfg.n_mel * h->n_frames;
   uint64_t up = 0, down = 0;
-  const int chunk = h->chunk_clips;
+  // Chunks of up to `cap` clips go through the ring; a small batch is cut finer so that the staging copy of one chunk
+  // overlaps the upload of the previous one (a batch of 8 as ONE chunk is staged, uploaded and computed back to back)
+  const int cap = h->chunk_clips;
+  int chunk = cap;
+  if (const char* e = getenv("WFE_HOST_CHUNK")) {
+    const int v = atoi(e);
+    if (v >= 1) chunk = v < cap ? v : cap;
+  } else if (batch < 4 * cap) {
+    chunk = (batch + 3) / 4;
+    if (chunk < 1) chunk = 1;
+  }
   int slot_i = 0;
   for (int c0 = 0; c0 < batch; c0 += chunk, slot_i = (slot_i + 1) % kSlots) {
     HostSlot& s = h->slots[slot_i];
@@ -937,7 +947,7 @@ int wfe_extract_host_ex(wfe_handle* h, const void* const* clips, const int64_t* 
     // ragged pack: only min(len, n_samples) samples of each clip cross PCIe; every clip starts on a 16-byte boundary
     // of the device buffer so that the kernels' vector / bulk-copy paths apply (starts in h_off[0..n), lengths after)
     int64_t* starts = s.h_off;
-    int64_t* lens = s.h_off + chunk;
+    int64_t* lens = s.h_off + cap;
     int64_t pos = 0, payload = 0;
     for (int i = 0; i < n; ++i) {
       int64_t len = lengths[c0 + i];
@@ -989,16 +999,16 @@ int wfe_extract_host_ex(wfe_handle* h, const void* const* clips, const int64_t* 
       }
     }
     up += (uint64_t)payload * es + (uint64_t)(2 * n) * sizeof(int64_t);
-    WFE_CUDA(cudaMemcpyAsync(s.d_off, s.h_off, (size_t)(2 * chunk) * sizeof(int64_t), cudaMemcpyHostToDevice, s.stream));
+    WFE_CUDA(cudaMemcpyAsync(s.d_off, s.h_off, (size_t)(2 * cap) * sizeof(int64_t), cudaMemcpyHostToDevice, s.stream));
     const float* stats = nullptr;
     if (do_normalize) {
-      rc = wfe_clip_stats(h, s.d_in, pcm_dtype, pcm_scale, s.d_off, s.d_off + chunk, n, s.d_stats, s.stream);
+      rc = wfe_clip_stats(h, s.d_in, pcm_dtype, pcm_scale, s.d_off, s.d_off + cap, n, s.d_stats, s.stream);
       if (rc != WFE_OK) return rc;
       stats = s.d_stats;
     }
     char* dst = static_cast<char*>(out) + (size_t)c0 * clip_out * os;
     int32_t* mdst = attn_mask ? attn_mask + (size_t)c0 * h->n_frames : nullptr;
-    rc = wfe_logmel_ex(h, s.d_in, pcm_dtype, pcm_scale, s.d_off, s.d_off + chunk, n, stats, out_device ? dst : s.d_out,
+    rc = wfe_logmel_ex(h, s.d_in, pcm_dtype, pcm_scale, s.d_off, s.d_off + cap, n, stats, out_device ? dst : s.d_out,
                        out_dtype, attn_mask ? (mask_device ? mdst : s.d_mask) : nullptr, s.d_scratch, s.stream);
     if (rc != WFE_OK) return rc;
     s.pending_out_bytes = (size_t)n * clip_out * os;
