@@ -578,3 +578,45 @@ def test_speechlike_batch_1024_against_the_oracle_on_64_clips(fe128):
     for b in range(0, B, 16):
         clip = pcm[starts[b]:starts[b] + lens[b]].cpu().numpy()
         assert np.abs(feats[b].cpu().numpy() - ologmel.logmel_clip(clip, 128, "fp64")).max() <= REGRESSION_TOL, b
+
+
+@pytest.mark.parametrize("batch", [1, 5, 8, 23, 70])
+def test_host_chunking_is_invisible(fe128, batch):
+    # the host entry cuts small batches into finer chunks (staging overlaps the upload): every batch size must give what
+    # the device entry gives on the same clips, bit for bit, whatever the chunk boundaries (1, 2, 2, 6, 16 clips here)
+    rng = np.random.default_rng(100 + batch)
+    clips = [np.array(signals.bursty(300 + i, int(n)), copy=True) for i, n in enumerate(rng.integers(2000, 480001, size=batch))]
+    host = fe128(clips, sampling_rate=16000, return_tensors="pt", return_attention_mask=True)
+    dev = fe128.cuda_device()
+    lens = np.array([len(c) for c in clips], dtype=np.int64)
+    starts = np.zeros(batch, dtype=np.int64)
+    np.cumsum((lens[:-1] + 7) & ~7, out=starts[1:])
+    pcm = torch.zeros(int(starts[-1] + lens[-1]) + 8, dtype=torch.float32, device=dev)
+    for c, o in zip(clips, starts):
+        pcm[o:o + len(c)] = torch.from_numpy(c).to(dev)
+    feats, mask = fe128.logmel_device(pcm, torch.from_numpy(starts).to(dev), batch, return_attention_mask=True,
+                                      lengths=torch.from_numpy(lens).to(dev))
+    assert fe128.debug_kernel_error() == 0
+    assert torch.equal(host["input_features"], feats.cpu())
+    assert torch.equal(host["attention_mask"], mask.cpu())
+    assert np.abs(feats[0].cpu().numpy() - ologmel.logmel_clip(clips[0], 128, "fp64")).max() <= REGRESSION_TOL
+
+
+def test_clamp_blocks_cover_every_element_below_the_floor(fe128):
+    # The clamp pass reads back only the 32-frame x 32-mel blocks whose published minimum is below the clip's floor: a
+    # clip with ONE loud frame and one quiet mel band elsewhere (most blocks untouched, a few with a single element to fix),
+    # a clip whose loud part comes last (every earlier tile was stored before the floor was known), and 80 mel (a partial
+    # last mel group) -- all against the oracle, and no element below max - 8 anywhere.
+    t = np.arange(480000) / 16000.0
+    quiet = (3e-5 * np.sin(2 * np.pi * 300.0 * t)).astype(np.float32)
+    a = quiet.copy()
+    a[240000:240400] += signals.noise(5, 400, amp=0.8)
+    b = quiet.copy()
+    b[470000:] += signals.noise(6, 10000, amp=0.5)
+    c = signals.click_in_silence()
+    clips = [a, b, c, signals.bursty(9)]
+    for n_mel, fe in ((128, fe128), (80, pkg.WhisperFeatureExtractor(feature_size=80))):
+        out = fe(clips, sampling_rate=16000, return_tensors="pt")["input_features"].numpy()
+        ref = ologmel.logmel_batch(clips, n_mel, "fp64")
+        assert np.abs(out - ref).max() <= REGRESSION_TOL, n_mel
+        assert (out.min(axis=(1, 2)) >= out.max(axis=(1, 2)) - 2.0 - 1e-6).all()
