@@ -252,11 +252,17 @@ class StreamingFrontendCollator:
             feats = fe(audio, sampling_rate=fe.sampling_rate, return_tensors="pt",
                        output_dtype=self.feature_dtype)["input_features"]
             return {"input_features": feats, "labels": fut()}
+        # CUDA tensors wanted (the in-loop consumer): the same overlap -- the helper thread packs, uploads and collates
+        # the labels while this one sits in the extractor's C entry (GIL released)
+        dev = fe.cuda_device()
+        if self._worker is None:
+            self._worker = _Worker()
+        fut = self._worker.submit(lambda: collate_labels_and_features(fe, label_lists, None, width=None,
+                                                                      decoder_start_token_id=-1, strip_bos=False,
+                                                                      device=dev)[1])
         out = fe(audio, sampling_rate=fe.sampling_rate, return_tensors="pt", output_device="cuda",
                  output_dtype=self.feature_dtype)
-        _, labels = collate_labels_and_features(fe, label_lists, None, width=None, decoder_start_token_id=-1,
-                                                strip_bos=False, device=out["input_features"].device)
-        return {"input_features": out["input_features"], "labels": labels}
+        return {"input_features": out["input_features"], "labels": fut()}
 
 
 def labels_fixed_length(fe, id_list: Sequence[int], max_length: int = 448) -> torch.Tensor:

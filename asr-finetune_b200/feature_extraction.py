@@ -116,6 +116,7 @@ class _Handle:
             pass
 
 
+_DIRECT_DTYPES = (np.dtype(np.float32), np.dtype(np.int16), np.dtype(np.float16))
 _OUT_DTYPES = {torch.float32: _lib.WFE_OUT_F32, torch.float16: _lib.WFE_OUT_F16, torch.bfloat16: _lib.WFE_OUT_BF16}
 
 
@@ -308,8 +309,11 @@ class WhisperFeatureExtractor:
         else:
             assert kinds == {np.dtype(np.float32)}, kinds
             dt = _lib.WFE_PCM_F32
-        ptrs = (C.c_void_p * B)(*[c.ctypes.data for c in clips])
-        lens = (C.c_int64 * B)(*[int(c.shape[0]) for c in clips])
+        # pointer / length tables through numpy (`ndarray.ctypes` builds a ctypes object per clip: 1 us each, and a
+        # training epoch makes this call for every batch)
+        ptr_tab = np.fromiter((c.__array_interface__["data"][0] for c in clips), dtype=np.uint64, count=B)
+        len_tab = np.fromiter((c.shape[0] for c in clips), dtype=np.int64, count=B)
+        ptrs, lens = ptr_tab.ctypes.data, len_tab.ctypes.data  # plain addresses (the tables live until the call returns)
         odt = _out_dtype(out_dtype)
         if to_device:  # the in-loop training consumer: the kernels write straight into CUDA tensors, nothing comes back
             out = torch.empty((B, h.n_mel, h.n_frames), dtype=odt, device=dev)
@@ -370,18 +374,24 @@ class WhisperFeatureExtractor:
                                              return_attention_mask, padding, max_length, do_normalize, output_device,
                                              output_dtype)
         seqs = list(raw_speech) if is_batched else [raw_speech]
-        clips = [np.asarray(s) for s in seqs]
-        # int16 / float16 PCM travels in its own width only when the WHOLE batch has that dtype (the kernels convert on
-        # load); anything else becomes float32 like HF does (fp64 / lists -> fp32, HF ...:282-286)
-        narrow = len({c.dtype for c in clips}) == 1 and clips[0].dtype in (np.int16, np.float16)
-        clips = [np.ascontiguousarray((c if narrow or c.dtype == np.float32 else c.astype(np.float32)).reshape(-1))
-                 for c in clips]
+        d0 = seqs[0].dtype if type(seqs[0]) is np.ndarray else None
+        if d0 in _DIRECT_DTYPES and all(type(s) is np.ndarray and s.dtype == d0 and s.ndim == 1 and s.flags.c_contiguous
+                                        for s in seqs):
+            clips = seqs  # what the reference's loader yields: nothing to convert, nothing to copy
+        else:
+            clips = [np.asarray(s) for s in seqs]
+            # int16 / float16 PCM travels in its own width only when the WHOLE batch has that dtype (the kernels convert
+            # on load); anything else becomes float32 like HF does (fp64 / lists -> fp32, HF ...:282-286)
+            narrow = len({c.dtype for c in clips}) == 1 and clips[0].dtype in (np.int16, np.float16)
+            clips = [np.ascontiguousarray((c if narrow or c.dtype == np.float32 else c.astype(np.float32)).reshape(-1))
+                     for c in clips]
 
         n_samples, lengths = self._resolve_length([int(c.shape[0]) for c in clips], truncation, padding, max_length,
                                                   pad_to_multiple_of)
         want_mask = bool(return_attention_mask if return_attention_mask is not None else self.return_attention_mask)
         norm = bool(do_normalize) if do_normalize is not None else bool(self.do_normalize)
-        clips = [c[:n] for c, n in zip(clips, lengths)]  # truncation (a no-op for clips that fit)
+        if any(c.shape[0] > n for c, n in zip(clips, lengths)):
+            clips = [c[:n] for c, n in zip(clips, lengths)]  # truncation
         if output_device is not None and str(output_device).startswith("cuda"):
             # host clips in, CUDA tensors out: the same pipelined upload (staging threads, three streams), no download
             feats, mask = self._extract_host(clips, n_samples, norm, want_mask, output_dtype, to_device=True)

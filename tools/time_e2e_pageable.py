@@ -22,3 +22,11 @@ m, mn = t(lambda: fe(clips, sampling_rate=16000, return_tensors="pt"))
 print(f"{tag}: fp32 pageable -> fp32 host: median {m:.2f} ms (min {mn:.2f})  {B*30/m*1e3/1e6:.3f} M audio-s/s")
 m, mn = t(lambda: fe(clips16, sampling_rate=16000, return_tensors="pt", output_dtype=torch.float16))
 print(f"{tag}: int16 pageable -> fp16 host: median {m:.2f} ms (min {mn:.2f})  {B*30/m*1e3/1e6:.3f} M audio-s/s")
+# the C entry alone (prebuilt pointer arrays, preallocated pinned output): what the Python shim adds is the difference
+import ctypes as C
+h = fe._handle(None, fe.cuda_device()); lib = pkg._lib.load()
+ptrs = (C.c_void_p * B)(*[c.ctypes.data for c in clips16]); lens = (C.c_int64 * B)(*[len(c) for c in clips16])
+out = torch.empty((B, 128, 3000), dtype=torch.float16, pin_memory=True)
+up, down = C.c_uint64(0), C.c_uint64(0)
+m, mn = t(lambda: lib.wfe_extract_host_ex(h.ptr, ptrs, lens, B, 1, 1.0 / 32768.0, 0, out.data_ptr(), 1, None, C.byref(up), C.byref(down)))
+print(f"{tag}: int16 -> fp16, wfe_extract_host_ex alone: median {m:.2f} ms (min {mn:.2f})  {B*30/m*1e3/1e6:.3f} M audio-s/s")
