@@ -75,7 +75,7 @@ constexpr int kThreads = 16 * 32;                // 8 epilogue workers, 4 prep w
 #ifndef WFE_TC_REGS_E
 #define WFE_TC_REGS_E 168
 #define WFE_TC_REGS_P 104
-#define WFE_TC_REGS_H 56
+#define WFE_TC_REGS_H 72
 #endif
 constexpr int kRegsLaunch = 128, kRegsE = WFE_TC_REGS_E, kRegsP = WFE_TC_REGS_P, kRegsH = WFE_TC_REGS_H;
 #ifndef WFE_TC_REGS_PROBE
@@ -86,7 +86,6 @@ constexpr int kTmemA = 4 * kN;                    // columns 448..511: A slots, 
 constexpr int kWarpMma = 12, kWarpLoad = 13, kWarpClamp = 14;
 constexpr int kRawBoxBytes = kRawRows * kRawPitch * 4;              // 85280: what one TMA delivers
 constexpr int kRawBufBytes = (kRawBoxBytes + 127) & ~127;           // 85376: TMA destinations are 128-byte aligned
-
 constexpr size_t kSmemRaw = 0;
 constexpr size_t kSmemB = kSmemRaw + 2 * (size_t)kRawBufBytes;       // 170752
 constexpr size_t kSmemTw = kSmemB + kBBytes;                         // +50176
@@ -361,14 +360,16 @@ __device__ __forceinline__ Tile tile_info(const TcParams& p, uint32_t id, int64_
   } else {
     // TMA: the whole 164 x 130 box (row pitch 160 floats) must lie inside the clip, start on a 16-byte boundary and
     // be addressable with an int32 element coordinate
-    const float* src = reinterpret_cast<const float*>(p.pcm) + t.off + s_begin;
+    const uintptr_t src = reinterpret_cast<uintptr_t>(reinterpret_cast<const float*>(p.pcm) + t.off + s_begin);
     // (the first tile of a clip starts 200 samples early: those land as whatever precedes the clip -- zeros if nothing
     //  does, the TMA fills out-of-range coordinates with zeros -- and are overwritten by the reflect pad afterwards)
     //  -- provided the clip does not start the buffer: the TMA bounds-checks the COORDINATE, not the address, and would
     //  zero-fill the head of every row whose column coordinate is negative)
-    const bool base_ok = p.pcm_dtype == 0 && p.norm == nullptr && (s_begin >= 0 || t.tile == 0) &&
-                         (reinterpret_cast<uintptr_t>(src) & 15u) == 0 && t.off + s_begin < (int64_t)0x7fff0000 &&
-                         t.off + s_begin >= 0;
+    // (2-byte PCM by TMA -- a box of 168 x 130 two-byte elements into the tail of the raw buffer, widened in place -- was
+    //  built and measured: ONE warp widening a tile needs 20-30 k cycles, twice the tile period, and the conversions cost
+    //  ~3.3 k warp-instructions per tile wherever they run; int16 / float16 PCM therefore stays on the generic path.)
+    const bool base_ok = p.pcm_dtype == 0 && p.norm == nullptr && (s_begin >= 0 || t.tile == 0) && (src & 15u) == 0 &&
+                         t.off + s_begin < (int64_t)0x7fff0000 && t.off + s_begin >= 0;
     const int box_end = s_begin + (kRawRows - 1) * kHop + kRawPitch;
     if (base_ok && box_end <= t.len)
       t.mode = s_begin >= 0 ? kModeAsync : kModeAsyncHead;
@@ -695,6 +696,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       const bool vec_ok = (p.pcm_dtype == 0 || p.pcm_dtype == 3) &&
                           ((reinterpret_cast<uintptr_t>(reinterpret_cast<const float*>(p.pcm) + tm.off + s_begin) & 15u) == 0);
+      const bool vec16_ok = (p.pcm_dtype == 1 || p.pcm_dtype == 2) &&
+                            ((reinterpret_cast<uintptr_t>(reinterpret_cast<const uint16_t*>(p.pcm) + tm.off + s_begin) & 7u) == 0);
       constexpr int kBatch = WFE_TC_STAGE_BATCH;  // quads of samples in flight per thread
       for (int g0 = wt; g0 < n_quads; g0 += 256 * kBatch) {
         float4 v[kBatch];
@@ -705,6 +708,16 @@ __global__ void __launch_bounds__(kThreads, 1)
           if (g0 + 256 * u < n_quads) {
             if (vec_ok && s >= 0 && s + 3 < tm.len) {  // interior (len <= n_samples: no reflection either)
               v[u] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.pcm) + tm.off + s));
+            } else if (vec16_ok && s >= 0 && s + 3 < tm.len) {  // the same for 2-byte PCM: four samples per 8-byte load
+              const uint2 w = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p.pcm) + tm.off + s));
+              if (p.pcm_dtype == 1) {
+                v[u] = make_float4((float)(int16_t)(w.x & 0xffffu) * p.pcm_scale, (float)(int16_t)(w.x >> 16) * p.pcm_scale,
+                                   (float)(int16_t)(w.y & 0xffffu) * p.pcm_scale, (float)(int16_t)(w.y >> 16) * p.pcm_scale);
+              } else {
+                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&w.x));
+                const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
+                v[u] = make_float4(a.x, a.y, c.x, c.y);
+              }
             } else {
               float e[4];
 #pragma unroll
@@ -1112,14 +1125,18 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (nt < 2) TCS(13, 2 + 3 * nt);
         ++tma_loads[rb];
         if (lane == 0) TCT(3, nt, 2);
+        // Edge patches, from the tile itself (the samples a reflection needs lie within 200 samples of the edge):
         if (t.mode == kModeAsyncHead) {
-          // first tile of a clip: the TMA started 200 samples before the clip; replace them by the centred reflect pad
+          // first tile of a clip: the TMA started 200 samples before the clip; replace them by the centred reflect pad,
+          // raw[i] = x[200 - i] = raw[400 - i] (zero where the clip is shorter than that)
           float v[7];
 #pragma unroll
           for (int u = 0; u < 7; ++u) {
-            const int i = lane + 32 * u, s = kNFft / 2 - i;  // raw[i] = x[200 - i]
-            v[u] = (i < kNFft / 2 && s < t.len) ? __ldg(reinterpret_cast<const float*>(p.pcm) + t.off + s) : 0.f;  // (TMA tiles are float32)
+            const int i = lane + 32 * u, j = kNFft - i;  // source index 201..400, rows 1 and 2
+            const int jr = j / kHop;
+            v[u] = (i < kNFft / 2 && kNFft / 2 - i < t.len) ? raw[jr * kRawPitch + (j - jr * kHop)] : 0.f;
           }
+          __syncwarp();
 #pragma unroll
           for (int u = 0; u < 7; ++u) {
             const int i = lane + 32 * u;
@@ -1132,7 +1149,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           // centred reflect pad; rows that no valid frame reads are zeroed too (the maximum is taken over the whole tile)
           const int s_begin = t.tile * kTileM * kHop - kNFft / 2;
           const int i0 = t.len - s_begin;  // first raw index past the clip (> 0: the tile is not silent)
-          // stores only (nothing here waits for memory): the rest of the clip's last row, then whole rows, 16 bytes at a time
+          // stores only: the rest of the clip's last row, then whole rows, 16 bytes at a time
           const int r0 = i0 / kHop, c0 = i0 - r0 * kHop;
           for (int c = c0 + lane; c < kHop; c += 32) raw[r0 * kRawPitch + c] = 0.f;
           for (int q = lane; q < (kRawRows - 1 - r0) * (kHop / 4); q += 32) {
@@ -1140,24 +1157,28 @@ __global__ void __launch_bounds__(kThreads, 1)
             *reinterpret_cast<float4*>(raw + r * kRawPitch + 4 * (q % (kHop / 4))) = make_float4(0.f, 0.f, 0.f, 0.f);
           }
           __syncwarp();
-          // reflect pad: raw index i <-> sample s = s_begin + i >= 480000 <-> source 2 * 479999 - s (at most 200 of them, and
-          // only when the clip is (nearly) full length); all loads first, then all stores
+          // reflect pad: raw index ir + k <-> sample 480000 + k <-> source sample 479998 - k = raw index ir - 2 - k (zero
+          // already where the clip is shorter); only the clip's last tile reaches sample 480000
           const int ir = kNSamples - s_begin;  // raw index of sample 480000
-          float v[7];
+          if (ir < kRawRows * kHop) {
+            float v[7];
 #pragma unroll
-          for (int u = 0; u < 7; ++u) {
-            const int sk = (kNSamples - 2) - (lane + 32 * u);  // source of raw index ir + lane + 32 u
-            v[u] = (lane + 32 * u < kNFft / 2 && sk >= 0 && sk < t.len) ? __ldg(reinterpret_cast<const float*>(p.pcm) + t.off + sk) : 0.f;
-          }
-#pragma unroll
-          for (int u = 0; u < 7; ++u) {
-            const int i = ir + lane + 32 * u;
-            if (lane + 32 * u < kNFft / 2 && i < kRawRows * kHop) {
-              const int r = i / kHop;
-              raw[r * kRawPitch + (i - r * kHop)] = v[u];
+            for (int u = 0; u < 7; ++u) {
+              const int k = lane + 32 * u, j = ir - 2 - k;
+              const int jr = j / kHop;
+              v[u] = (k < kNFft / 2 && j >= 0) ? raw[jr * kRawPitch + (j - jr * kHop)] : 0.f;
             }
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < 7; ++u) {
+              const int i = ir + lane + 32 * u;
+              if (lane + 32 * u < kNFft / 2 && i < kRawRows * kHop) {
+                const int r = i / kHop;
+                raw[r * kRawPitch + (i - r * kHop)] = v[u];
+              }
+            }
+            __syncwarp();
           }
-          __syncwarp();
         }
       }
       if (lane == 0) {

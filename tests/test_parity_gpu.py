@@ -620,3 +620,35 @@ def test_clamp_blocks_cover_every_element_below_the_floor(fe128):
         ref = ologmel.logmel_batch(clips, n_mel, "fp64")
         assert np.abs(out - ref).max() <= REGRESSION_TOL, n_mel
         assert (out.min(axis=(1, 2)) >= out.max(axis=(1, 2)) - 2.0 - 1e-6).all()
+
+
+@pytest.mark.parametrize("dtype", ["int16", "float16"])
+def test_two_byte_pcm_aligned_and_unaligned_agree_with_the_oracle(fe128, dtype):
+    # int16 / float16 PCM resident on the device is staged by the workers (four samples per 8-byte load when the clip
+    # starts on an 8-byte boundary, sample by sample otherwise); clip heads and tails included.  Both layouts against the
+    # oracle on the dequantised samples, for lengths around tile / hop-row boundaries and full-length clips (reflect pad
+    # at sample 480000).
+    lens = [480000, 479999, 479841, 470841, 470840, 20480, 20481, 20319, 164039, 164040, 164041, 300007, 480000, 77, 480000]
+    f32 = [signals.bursty(400 + i, n) for i, n in enumerate(lens)]
+    if dtype == "int16":
+        q = [np.clip(np.round(c * 32767.0), -32768, 32767).astype(np.int16) for c in f32]
+        deq = [(c.astype(np.float32) * np.float32(1.0 / 32768.0)) for c in q]
+        tdt, scale = torch.int16, 1.0 / 32768.0
+    else:
+        q = [c.astype(np.float16) for c in f32]
+        deq = [c.astype(np.float32) for c in q]
+        tdt, scale = torch.float16, 1.0
+    dev = fe128.cuda_device()
+    ref = ologmel.logmel_batch(deq, 128, "fp64")
+    mref = ologmel.frame_attention_mask(lens)
+    for align in (8, 1):  # 8 elements = 16 bytes (vector loads), 1 element = sample by sample
+        starts = np.zeros(len(lens), dtype=np.int64)
+        np.cumsum([(n + align - 1) // align * align + (0 if align == 8 else 1) for n in lens[:-1]], out=starts[1:])
+        pcm = torch.zeros(int(starts[-1] + lens[-1]), dtype=tdt, device=dev)
+        for c, o in zip(q, starts):
+            pcm[o:o + len(c)] = torch.from_numpy(c).to(dev)
+        feats, mask = fe128.logmel_device(pcm, torch.from_numpy(starts).to(dev), len(lens), return_attention_mask=True,
+                                          lengths=torch.tensor(lens, dtype=torch.int64, device=dev), pcm_scale=scale)
+        assert fe128.debug_kernel_error() == 0
+        assert np.abs(feats.cpu().numpy() - ref).max() <= REGRESSION_TOL, align
+        assert np.array_equal(mask.cpu().numpy(), mref), align

@@ -15,6 +15,10 @@ pcm = 0.1 * torch.randn(B * 480000, device=dev, generator=g)
 if kind == "bursty":  # speech-like dynamics: 0.2 s segments with random gains over 60 dB
     seg = torch.rand(B * 480000 // 3200, device=dev, generator=g)
     pcm = pcm * torch.repeat_interleave(10.0 ** (-3.0 * seg), 3200)
+if kind == "int16":  # device-resident int16 PCM
+    pcm = (pcm.clamp(-1, 1) * 32767).to(torch.int16)
+if kind == "fp16":
+    pcm = pcm.to(torch.float16)
 offs = torch.arange(B + 1, dtype=torch.int64, device=dev) * 480000
 lengths = None
 audio_s = B * 30.0
