@@ -106,9 +106,6 @@ constexpr size_t kSmemBytes = kSmemWs + 2 * kWsFloats * 4;           // 225760 (
 #undef WFE_TC_GEN_COUNTS
 constexpr int kMaxShared = kTcShared80 > kTcShared128 ? kTcShared80 : kTcShared128;  // filters fed by both epilogue halves
 
-#ifndef WFE_TC_STAGE_BATCH
-#define WFE_TC_STAGE_BATCH 2  // (8 in flight cost 1500 more SASS instructions and, although rarely run, 3 % of the kernel's speed)
-#endif
 #ifndef WFE_TC_TRACE_CTA
 #define WFE_TC_TRACE_CTA 0
 #endif
@@ -694,61 +691,78 @@ __global__ void __launch_bounds__(kThreads, 1)
         mean = st.x;
         rstd = st.y;
       }
-      const bool vec_ok = (p.pcm_dtype == 0 || p.pcm_dtype == 3) &&
-                          ((reinterpret_cast<uintptr_t>(reinterpret_cast<const float*>(p.pcm) + tm.off + s_begin) & 15u) == 0);
-      const bool vec16_ok = (p.pcm_dtype == 1 || p.pcm_dtype == 2) &&
-                            ((reinterpret_cast<uintptr_t>(reinterpret_cast<const uint16_t*>(p.pcm) + tm.off + s_begin) & 7u) == 0);
-      constexpr int kBatch = WFE_TC_STAGE_BATCH;  // quads of samples in flight per thread
-      for (int g0 = wt; g0 < n_quads; g0 += 256 * kBatch) {
-        float4 v[kBatch];
+      // Quads [q_lo, q_hi) lie wholly inside the clip (no reflection, no zero padding) and, when the clip starts on a
+      // 16-byte (float32) / 8-byte (2-byte PCM) boundary, are one vector load each: eight per thread in flight.  The few
+      // quads around the clip's edges -- and everything of a clip at an odd address -- go sample by sample in a rolled
+      // loop: small code matters more here than speed (the kernel is instruction-fetch sensitive).
+      const int es = (p.pcm_dtype == 0 || p.pcm_dtype == 3) ? 4 : 2;
+      const uintptr_t first = reinterpret_cast<uintptr_t>(p.pcm) + (uintptr_t)((tm.off + s_begin) * es);
+      const bool vec_ok = (first & (es == 4 ? 15u : 7u)) == 0;
+      const int q_lo = vec_ok ? min(n_quads, s_begin < 0 ? (-s_begin + 3) / 4 : 0) : n_quads;
+      const int q_hi = vec_ok ? max(q_lo, min(n_quads, (tm.len - s_begin) / 4)) : n_quads;
+      auto put = [&](int g, float4 x) {
+        const int r = g / (kHop / 4);
+        *reinterpret_cast<float4*>(raw + r * kRawPitch + 4 * (g - r * (kHop / 4))) = x;
+      };
+      constexpr int kBatch = 8;
+      for (int g0 = q_lo + wt; g0 < q_hi; g0 += 256 * kBatch) {
+        uint4 v[kBatch];
 #pragma unroll
         for (int u = 0; u < kBatch; ++u) {
-          const int s = s_begin + 4 * (g0 + 256 * u);
-          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (g0 + 256 * u < n_quads) {
-            if (vec_ok && s >= 0 && s + 3 < tm.len) {  // interior (len <= n_samples: no reflection either)
-              v[u] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.pcm) + tm.off + s));
-            } else if (vec16_ok && s >= 0 && s + 3 < tm.len) {  // the same for 2-byte PCM: four samples per 8-byte load
-              const uint2 w = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p.pcm) + tm.off + s));
-              if (p.pcm_dtype == 1) {
-                v[u] = make_float4((float)(int16_t)(w.x & 0xffffu) * p.pcm_scale, (float)(int16_t)(w.x >> 16) * p.pcm_scale,
-                                   (float)(int16_t)(w.y & 0xffffu) * p.pcm_scale, (float)(int16_t)(w.y >> 16) * p.pcm_scale);
-              } else {
-                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&w.x));
-                const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
-                v[u] = make_float4(a.x, a.y, c.x, c.y);
-              }
-            } else {
-              float e[4];
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                int sk = s + k;
-                if (sk < 0) sk = -sk;
-                if (sk >= kNSamples) sk = 2 * (kNSamples - 1) - sk;
-                e[k] = (sk >= 0 && sk < tm.len) ? load_pcm(p.pcm, p.pcm_dtype, tm.off + sk, p.pcm_scale) : 0.f;
-              }
-              v[u] = make_float4(e[0], e[1], e[2], e[3]);
-            }
+          const int g = min(g0 + 256 * u, q_hi - 1);  // (re-reading the last quad is harmless)
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(first) + (size_t)(4 * g) * es;
+          if (es == 4) {
+            v[u] = __ldg(reinterpret_cast<const uint4*>(src));
+          } else {
+            const uint2 w = __ldg(reinterpret_cast<const uint2*>(src));
+            v[u] = make_uint4(w.x, w.y, 0u, 0u);
           }
         }
 #pragma unroll
         for (int u = 0; u < kBatch; ++u) {
           const int g = g0 + 256 * u;
-          if (g < n_quads) {
-            float4 x = v[u];
-            if (p.norm != nullptr) {
-              const int s = s_begin + 4 * g;
-              float* e = reinterpret_cast<float*>(&x);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                int sk = s + k;
-                if (sk < 0) sk = -sk;
-                if (sk >= kNSamples) sk = 2 * (kNSamples - 1) - sk;
-                if (sk >= 0 && sk < tm.len) e[k] = (e[k] - mean) * rstd;
-              }
-            }
-            const int r = g / (kHop / 4);
-            *reinterpret_cast<float4*>(raw + r * kRawPitch + 4 * (g - r * (kHop / 4))) = x;
+          if (g >= q_hi) continue;
+          float4 x;
+          if (es == 4) {
+            x = make_float4(__uint_as_float(v[u].x), __uint_as_float(v[u].y), __uint_as_float(v[u].z), __uint_as_float(v[u].w));
+          } else if (p.pcm_dtype == 1) {
+            x = make_float4((float)(int16_t)(v[u].x & 0xffffu) * p.pcm_scale, (float)(int16_t)(v[u].x >> 16) * p.pcm_scale,
+                            (float)(int16_t)(v[u].y & 0xffffu) * p.pcm_scale, (float)(int16_t)(v[u].y >> 16) * p.pcm_scale);
+          } else {
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v[u].x));
+            const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&v[u].y));
+            x = make_float4(a.x, a.y, c.x, c.y);
+          }
+          put(g, x);
+        }
+      }
+      // the edges: quads [0, q_lo) and [q_hi, n_quads)
+#pragma unroll 1
+      for (int g = wt; g < q_lo + (n_quads - q_hi); g += 256) {
+        const int gq = g < q_lo ? g : g - q_lo + q_hi;
+        float e[4];
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+          int sk = s_begin + 4 * gq + k;
+          if (sk < 0) sk = -sk;
+          if (sk >= kNSamples) sk = 2 * (kNSamples - 1) - sk;
+          e[k] = (sk >= 0 && sk < tm.len) ? load_pcm(p.pcm, p.pcm_dtype, tm.off + sk, p.pcm_scale) : 0.f;
+        }
+        put(gq, make_float4(e[0], e[1], e[2], e[3]));
+      }
+      if (p.norm != nullptr) {
+        // zero-mean / unit-variance (do_normalize): every sample of the clip, i.e. not the zero padding -- each thread
+        // revisits the quads it has just written
+#pragma unroll 1
+        for (int g = wt; g < n_quads; g += 256) {
+          const int r = g / (kHop / 4);
+          float* e = raw + r * kRawPitch + 4 * (g - r * (kHop / 4));
+#pragma unroll 1
+          for (int k = 0; k < 4; ++k) {
+            int sk = s_begin + 4 * g + k;
+            if (sk < 0) sk = -sk;
+            if (sk >= kNSamples) sk = 2 * (kNSamples - 1) - sk;
+            if (sk >= 0 && sk < tm.len) e[k] = (e[k] - mean) * rstd;
           }
         }
       }
