@@ -475,8 +475,8 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
       //     pending tiles (lane l reads words l, l+32, l+64, l+96); all consumed at the end of the block
       int64_t g_off = 0, g_avail = 0;
       if (lane == 0) request_clip(p, idB, g_off, g_avail);
-      const int chk0 = ring_count > 0 ? s_pend_bt[ring_head].x : -1;
-      const int chk1 = ring_count > 1 ? s_pend_bt[(ring_head + 1) & (kRing - 1)].x : -1;
+      int chk0 = ring_count > 0 ? s_pend_bt[ring_head].x : -1;
+      int chk1 = ring_count > 1 ? s_pend_bt[(ring_head + 1) & (kRing - 1)].x : -1;
       uint32_t k0[4], k1[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -502,6 +502,9 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
             const FixEntry fx{bt.x, bt.y & ~kSilentBit, fl, (bt.y & kSilentBit) != 0 || pm.y <= fl};
             fix_tile(p.out, p.n_mel, p.n_frames, fx, 0, 1, lane);
           }
+          // the words read in (1) belong to the entry just popped and to its successor: the head has moved, so step (3)
+          // must not pair them with the NEW head this time round
+          chk0 = chk1 = -1;
         }
         if (lane == 0) {
           st_relaxed_u32(p.tile_key + (size_t)prev_b * p.ntiles + prev_tile, f2key(mx));
