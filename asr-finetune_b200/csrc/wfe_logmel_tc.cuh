@@ -26,21 +26,26 @@
 //
 //   * TMEM is full (4 x 112 accumulator columns + 64 operand columns of 512), so the accumulators cannot be double-
 //     buffered: a tile's MMA phase and its epilogue phase alternate.  Both phases are latency-bound per warp, so the
-//     eight WORKER warps (two per SM sub-partition and TMEM lane quarter) take part in BOTH: in the MMA phase the two
-//     warps of a quarter prepare alternate k-steps; in the epilogue each takes half of the k2 range, and the few mel
+//     eight EPILOGUE warps (two per SM sub-partition and TMEM lane quarter) take part in BOTH: in the MMA phase they
+//     prepare k-steps 3..6 (the prep warps 0..2); in the epilogue each takes half of the k2 range, and the few mel
 //     filters fed by both halves are completed through a 2.5 KB shared-memory exchange.
 //
-// One persistent CTA per SM, 11 warps, tile = 128 consecutive frames of one clip (24 tiles per 30-s clip), tile ids
-// strided statically over the CTAs (every role derives the same sequence):
-//   warps 0-7   WORKERS   thread = frame = TMEM lane (quarter = warp % 4, half = warp / 4)
-//               prep:     raw samples (smem) -> scale, window (FMUL immediates), split hi/lo -> TMEM (tcgen05.st)
+// One persistent CTA per SM, 16 warps, tile = 128 consecutive frames of one clip (24 tiles per 30-s clip); tile ids come
+// from a global counter (the SMs do not run at the same pace), the loader hands each tile's geometry to everybody:
+//   warps 0-7   EPILOGUE WORKERS   thread = frame = TMEM lane (quarter = warp % 4, half = warp / 4); 168 registers
+//               MMA phase: two k-steps each (half 1: k3, k5; half 0: k4, k6): raw samples (smem) x scaled window, split
+//                         hi / lo (packed f32x2) -> TMEM (tcgen05.st)
 //               epilogue: tcgen05.ld, twiddle + DFT-4 + power (packed f32x2), banded mel with immediate weights
-//                         (generated straight-line code), log10, (x+4)/4, store, tile min/max
-//   warp  8     MMA       one elected lane issues 3 tcgen05.mma per (k-step, n1) slot, commits to mbarriers
-//   warp  9     LOADER    one TMA per tile
-//   warp 14     BOOKS     publishes each tile's maximum and minimum for the clamp pass (clamp_kernel)
+//                         (generated straight-line code), log10, (x+4)/4, store, tile maximum + per-block minima
+//   warps 8-11  PREP WORKERS       k-steps 0, 1, 2 of every tile (k0, k1 of the NEXT tile in the epilogue's shadow), then
+//                                  the next tile's max |x| -> power-of-two scale -> scaled window table; 104 registers
+//   warp 12     MMA ISSUER         one elected lane issues 3 tcgen05.mma per (k-step, n1) slot, commits to mbarriers
+//   warp 13     LOADER             next tile id, one TMA per tile, clip-edge patches from the landed tile, tile meta data
+//   warp 14     BOOKS              publishes each tile's maximum and block minima for the clamp pass (clamp_kernel)
+//   warp 15     idle               (every scheduler must start with four warps' worth of registers); 12-14: 72 registers
 // Specialised for n_samples = 480000 (3000 frames), n_mel in {80, 128} with the slaney structure baked by
-// tools/gen_tc_epilogue.py; everything else runs on the CUDA-core kernel.
+// tools/gen_tc_epilogue.py; everything else runs on the CUDA-core kernel.  The kernel is instruction-fetch sensitive:
+// code that rarely runs is kept small and rolled.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
