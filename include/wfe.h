@@ -164,9 +164,10 @@ int wfe_collate(wfe_handle* h, const int64_t* ids, const int64_t* offsets, int32
  *            downloaded -- the in-loop training consumer (host clips in, CUDA tensors out)
  * attn_mask  HOST (or DEVICE, like `out`) int32 (batch, n_frames) or NULL
  * do_normalize  0/1 (zero-mean unit-variance per clip before the STFT)
- * Work is cut into chunks of clips and pipelined: pinned staging -> H2D -> kernels -> D2H on the handle's
- * private streams; pageable clips are staged by a few persistent copy threads (WFE_HOST_THREADS, default
- * min(8, cores / 2)).  Synchronous: returns when `out` is complete.  h2d_bytes/d2h_bytes (may be NULL) receive
+ * Work is cut into chunks of clips (16; a quarter of the batch below 64 clips; WFE_HOST_CHUNK overrides) and
+ * pipelined: pinned staging -> H2D -> kernels -> D2H on the handle's private streams; pageable clips are staged by a
+ * few persistent copy threads (WFE_HOST_THREADS, default min(8, cores / 2)).  Clips are uploaded straight from the
+ * caller's memory only when the batch STARTS with a pinned clip (the driver is then asked about every clip).  Synchronous: returns when `out` is complete.  h2d_bytes/d2h_bytes (may be NULL) receive
  * the bytes that crossed PCIe.
  */
 int wfe_extract_host(wfe_handle* h, const void* const* clips, const int64_t* lengths, int32_t batch,
