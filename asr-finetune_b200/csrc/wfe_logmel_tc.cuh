@@ -1169,8 +1169,11 @@ __global__ void __launch_bounds__(kThreads, 1)
           const int s_begin = t.tile * kTileM * kHop - kNFft / 2;
           const int i0 = t.len - s_begin;  // first raw index past the clip (> 0: the tile is not silent)
           // stores only: the rest of the clip's last row, then whole rows, 16 bytes at a time
+          // (a clip that ends inside the four pad columns of the box's last row has i0 = 130 * 160 .. + 3: every sample a
+          //  frame reads is real, nothing to zero -- and row 130 would be the first row of the NEXT buffer, or of B)
           const int r0 = i0 / kHop, c0 = i0 - r0 * kHop;
-          for (int c = c0 + lane; c < kHop; c += 32) raw[r0 * kRawPitch + c] = 0.f;
+          if (r0 < kRawRows)
+            for (int c = c0 + lane; c < kHop; c += 32) raw[r0 * kRawPitch + c] = 0.f;
           for (int q = lane; q < (kRawRows - 1 - r0) * (kHop / 4); q += 32) {
             const int r = r0 + 1 + q / (kHop / 4);
             *reinterpret_cast<float4*>(raw + r * kRawPitch + 4 * (q % (kHop / 4))) = make_float4(0.f, 0.f, 0.f, 0.f);

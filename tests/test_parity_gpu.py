@@ -22,6 +22,21 @@ TOL = 1e-3  # north_star tolerance on (log10(mel)+4)/4 features
 # fp16 tensor-core DFT + lg2.approx); a change that costs accuracy must show up long before it reaches 1e-3.
 REGRESSION_TOL = 2e-4
 
+
+def _cuda_core_kernel(fe, monkeypatch, *args, **kwargs):
+    """The same device-resident call on the CUDA-core kernel (WFE_DISABLE_TC=1): an independent implementation of the
+    same arithmetic, cheap enough to cross-check EVERY clip of a full-size batch on the GPU (the CPU oracle covers a
+    sample of them).  Both kernels are within REGRESSION_TOL of the oracle, so they agree within TOL everywhere."""
+    monkeypatch.setenv("WFE_DISABLE_TC", "1")
+    try:
+        assert not fe.uses_tensor_cores()
+        out = fe.logmel_device(*args, **kwargs)
+        torch.cuda.synchronize()
+    finally:
+        monkeypatch.delenv("WFE_DISABLE_TC")
+    assert fe.uses_tensor_cores()
+    return out
+
 import asr_finetune_b200 as pkg  # noqa: E402
 
 
@@ -396,7 +411,7 @@ def test_in_loop_training_consumer_tiny_whisper(fe80):
     assert torch.isfinite(loss) and model.model.encoder.conv1.weight.grad is not None
 
 
-def test_config3_full_size_batch_1024_properties(fe128):
+def test_config3_full_size_batch_1024_properties(fe128, monkeypatch):
     # BASELINE configs[2] at its full size: 1024 ragged clips (1-30 s) + labels; size-independent properties on every
     # clip, the oracle on a few.  (~1 GB of PCM, 1.57 GB of features)
     B = 1024
@@ -418,9 +433,21 @@ def test_config3_full_size_batch_1024_properties(fe128):
     tcol = torch.arange(3000, device=dev)[None, :]
     silent = tcol >= t_sil[:, None]
     assert bool(((feats == floor[:, None, None]) | ~silent[:, None, :]).all())
-    for b in (0, 511, 1023):
+    assert fe128.debug_kernel_error() == 0
+    for b in (0, 511, 669, 1023):  # (clip 669 ends inside the pad columns of its tail tile's TMA box)
         clip = pcm[starts[b]:starts[b] + lens[b]].cpu().numpy()
         assert np.abs(feats[b].cpu().numpy() - ologmel.logmel_clip(clip, 128, "fp64")).max() <= TOL, b
+    # every clip: against the CUDA-core kernel, and run to run (a stray shared-memory write shows up as one wrong frame
+    # or tile somewhere in the batch, in a clip no sample of three would hit)
+    feats_cc, _ = _cuda_core_kernel(fe128, monkeypatch, pcm, torch.from_numpy(starts).to(dev), B,
+                                    lengths=torch.from_numpy(lens).to(dev))
+    per_clip = (feats - feats_cc).abs().amax(dim=(1, 2))
+    assert float(per_clip.max()) <= TOL, torch.nonzero(per_clip > TOL).flatten().tolist()[:16]
+    del feats_cc
+    for _ in range(2):
+        again, _ = fe128.logmel_device(pcm, torch.from_numpy(starts).to(dev), B, lengths=torch.from_numpy(lens).to(dev))
+        assert torch.equal(again, feats)
+    del again
     labels = signals.label_ids(1337, B, 5, 448)
     coll = pkg.DataCollatorSpeechSeq2SeqWithPadding(processor=type("P", (), {"feature_extractor": fe128})(),
                                                     decoder_start_token_id=signals.SOT)
@@ -555,7 +582,45 @@ def test_clip_tails_by_tma_and_by_staging_agree_with_the_oracle(fe128):
         assert np.array_equal(mask.cpu().numpy(), mref), align
 
 
-def test_speechlike_batch_1024_against_the_oracle_on_64_clips(fe128):
+def test_clip_ending_in_the_pad_columns_of_its_tail_tile(fe128, monkeypatch):
+    # The TMA box of a tile is 130 rows of 164 floats over a 160-float pitch: the last 4 floats of its last row alias the
+    # first 4 samples of "row 130".  A clip that ends exactly there (len - tile start in 20800..20803) needs no patch at
+    # all; the loader's zero fill used to start at row 130 -- the first row of the other raw buffer, or of the DFT operand
+    # B behind the second one, which corrupted every later tile of that CTA.  Many such clips among ordinary ones, enough
+    # tiles for several per CTA, every clip checked (the damage lands in OTHER tiles than the one that causes it).
+    rng = np.random.default_rng(5)
+    lens = []
+    for i in range(96):
+        if i % 3 == 0:
+            t = 1 + (i // 3) % 22
+            lens.append(t * 20480 - 200 + 20800 + (i // 3) % 4)
+        else:
+            lens.append(int(rng.integers(16000, 480001)))
+    B = len(lens)
+    lens = np.asarray(lens, dtype=np.int64)
+    dev = fe128.cuda_device()
+    starts = np.zeros(B, dtype=np.int64)
+    np.cumsum((lens[:-1] + 3) & ~3, out=starts[1:])
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
+    pcm = 0.1 * torch.randn(int(starts[-1] + lens[-1]), device=dev, generator=g)
+    d_starts, d_lens = torch.from_numpy(starts).to(dev), torch.from_numpy(lens).to(dev)
+    feats_cc, _ = _cuda_core_kernel(fe128, monkeypatch, pcm, d_starts, B, lengths=d_lens)
+    first = None
+    for _ in range(4):  # which CTA (and which of its two raw buffers) takes a tile changes from run to run
+        feats, mask = fe128.logmel_device(pcm, d_starts, B, return_attention_mask=True, lengths=d_lens)
+        assert fe128.debug_kernel_error() == 0
+        per_clip = (feats - feats_cc).abs().amax(dim=(1, 2))
+        assert float(per_clip.max()) <= TOL, torch.nonzero(per_clip > TOL).flatten().tolist()[:16]
+        assert first is None or torch.equal(feats, first)
+        first = feats
+    assert torch.equal(mask.cpu(), torch.from_numpy(ologmel.frame_attention_mask(lens)))
+    for b in (0, 3, 30, 63, 93):
+        clip = pcm[starts[b]:starts[b] + lens[b]].cpu().numpy()
+        assert np.abs(first[b].cpu().numpy() - ologmel.logmel_clip(clip, 128, "fp64")).max() <= REGRESSION_TOL, b
+
+
+def test_speechlike_batch_1024_against_the_oracle_on_64_clips(fe128, monkeypatch):
     # BASELINE configs[2] size with the data-dependent path busy: 1024 ragged clips with speech-like dynamics (the clamp
     # pass rewrites most tiles), 64 of them against the oracle, all of them by the device-side invariants
     B = 1024
@@ -572,6 +637,12 @@ def test_speechlike_batch_1024_against_the_oracle_on_64_clips(fe128):
                                       lengths=torch.from_numpy(lens).to(dev))
     feats2, _ = fe128.logmel_device(pcm, torch.from_numpy(starts).to(dev), B, lengths=torch.from_numpy(lens).to(dev))
     assert torch.equal(feats, feats2)  # run-to-run identical
+    del feats2
+    feats_cc, _ = _cuda_core_kernel(fe128, monkeypatch, pcm, torch.from_numpy(starts).to(dev), B,
+                                    lengths=torch.from_numpy(lens).to(dev))
+    per_clip = (feats - feats_cc).abs().amax(dim=(1, 2))  # every clip against the independent CUDA-core kernel
+    assert float(per_clip.max()) <= TOL, torch.nonzero(per_clip > TOL).flatten().tolist()[:16]
+    del feats_cc
     gmax = feats.amax(dim=(1, 2))
     assert torch.isfinite(feats).all() and bool((feats.amin(dim=(1, 2)) >= gmax - 2.0).all())
     assert torch.equal(mask.cpu(), torch.from_numpy(ologmel.frame_attention_mask(lens)))
