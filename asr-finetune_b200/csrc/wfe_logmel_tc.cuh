@@ -413,6 +413,7 @@ __device__ __forceinline__ float from_out<__nv_bfloat16>(__nv_bfloat16 v) { retu
 //  one warp became the bottleneck: 15.0 M audio-s/s against 21.1 M on noise.)
 // ---------------------------------------------------------------------------------------------------------------
 constexpr uint32_t kMinSilent = 0x7fc00001u;
+constexpr uint32_t kBooksDone = 0xffffffffu;  // s_red_id: no more tiles
 constexpr int kClampThreads = 256;
 // a tile's minima are published per BLOCK of 32 frames (one epilogue warp's quarter) x 32 mel rows: on speech-like audio
 // nearly every 128-frame tile holds a few elements below its clip's floor (0.3 % of all elements, 95 % of the tiles),
@@ -615,6 +616,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   __shared__ uint32_t s_pmax[8];        // generic staging: per-warp max |x| bits
   __shared__ uint32_t s_tilemax[2];     // per raw buffer: max |x| bits of the tile (atomicMax by the worker warps)
   __shared__ float2 s_scale[2];         // per raw buffer: (power-of-two scale, log-domain constant) of the tile
+  __shared__ uint32_t s_red_id[2];      // [tile parity] id (clip * 24 + tile) of the tile whose extrema are in s_red, or kBooksDone
   __shared__ float s_red[2][1 + kMinGroups][8];  // [tile parity][max, min of mel group 0..3][worker warp] of y over the warp's share of the tile
   __shared__ float s_part[(kNMel == 128 ? kTcShared128 : kTcShared80) * kTileM];  // epilogue half 1 -> half 0: partial sums of the shared mel filters
 
@@ -756,8 +758,11 @@ __global__ void __launch_bounds__(kThreads, 1)
         put(gq, make_float4(e[0], e[1], e[2], e[3]));
       }
       if (p.norm != nullptr) {
-        // zero-mean / unit-variance (do_normalize): every sample of the clip, i.e. not the zero padding -- each thread
-        // revisits the quads it has just written
+        // zero-mean / unit-variance (do_normalize): every sample of the clip, i.e. not the zero padding.  Thread wt takes
+        // the quads g = wt (mod 256), which OTHER threads wrote above whenever q_lo or q_hi is not a multiple of 256 (a
+        // clip's first tile: q_lo = 50): without the barrier a fast warp normalised quads a slow one had not written yet
+        // and the raw samples landed on top (found by tools/fuzz_tc_vs_cc.py: 3 of 3500 normalised batches).
+        worker_bar();
 #pragma unroll 1
         for (int g = wt; g < n_quads; g += 256) {
           const int r = g / (kHop / 4);
@@ -962,6 +967,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
         for (int g = 0; g < kMinGroups; ++g)
           s_red[nt & 1u][1 + g][warp] = fmaf(lg2_approx(__uint_as_float(rming[g])), 0.25f * kLog10_2, tile_k);
+        if (warp == 0) s_red_id[nt & 1u] = (uint32_t)cur.b * (uint32_t)kNTiles + (uint32_t)cur.tile;
         __threadfence_block();
         mbar_arrive(&bar_st_full[nt & 1u]);  // release: the tile's global stores (ordered by __syncwarp) and s_red
       }
@@ -969,6 +975,15 @@ __global__ void __launch_bounds__(kThreads, 1)
       cur = nxt;
       ++nt;
       if (cur.mode == kModeDone) break;
+    }
+    // no more tiles: tell the books warp through the same channel (it never looks at the loader's meta data, whose slot
+    // the loader may already have refilled by the time the books warp gets to it)
+    mbar_wait(&bar_st_empty[nt & 1u], ((nt >> 1) & 1u) ^ 1u, err_flag);
+    __syncwarp();
+    if (lane == 0) {
+      if (warp == 0) s_red_id[nt & 1u] = kBooksDone;
+      __threadfence_block();
+      mbar_arrive(&bar_st_full[nt & 1u]);
     }
   } else if (warp < 12) {
     // ======================================== PREP WORKERS ========================================
@@ -1227,39 +1242,28 @@ __global__ void __launch_bounds__(kThreads, 1)
   } else if (warp == kWarpClamp) {
     reg_shrink<kRegsH>();
     // =========================================== CLAMP BOOKS ===========================================
-    // Publishes every tile's extrema for the clamp pass (clamp_kernel) and writes the attention mask of padding tiles.
+    // Publishes every computed tile's extrema for the clamp pass (clamp_kernel).  Tile id and extrema both come from the
+    // epilogue workers (s_red_id, s_red), handed over by bar_st_full / bar_st_empty.  (Up to round-2 v22 the id was read
+    // from the loader's s_meta slot, which the loader refills as soon as the workers have finished READING the tile's raw
+    // samples -- immediately when no TMA is needed: the end-of-work marker, a staged tile.  A books warp that was a
+    // thousand cycles late then published under the wrong id, or left early, and the clamp pass read stale words for
+    // that tile: wrong clamping in a few blocks, once in a few thousand ragged batches -- tools/fuzz_tc_vs_cc.py.)
     uint32_t nt = 0;
     for (;;) {
-      // (the tile's meta data stays in s_meta until the workers have finished reading its raw samples: long enough)
-      mbar_wait<WFE_TC_SLEEP_LONG>(&bar_meta_full[nt & 1u], (nt >> 1) & 1u, err_flag);
-      Tile t;
-      t.b = s_meta[nt & 1u].b;
-      t.tile = s_meta[nt & 1u].tile;
-      t.mode = s_meta[nt & 1u].mode;
-      if (t.mode == kModeDone) break;
-      const uint32_t id = (uint32_t)t.b * (uint32_t)kNTiles + (uint32_t)t.tile;
-      float mx;
-      uint32_t mnb;  // lanes 0..15: minimum of block (frame quarter lane / 4, mel group lane % 4)
-      if (t.mode == kModeSilent) {
-        mx = -1.5f;  // (log10(1e-10) + 4) / 4: what the reference computes for zero padding
-        mnb = kMinSilent;
-        if (p.mask != nullptr) {
-          const int t0 = t.tile * kTileM;
-          for (int f = lane; f < kTileM && t0 + f < kNFrames; f += 32) p.mask[(size_t)t.b * kNFrames + t0 + f] = 0;
-        }
-      } else {
-        mbar_wait<WFE_TC_SLEEP_LONG>(&bar_st_full[nt & 1u], (nt >> 1) & 1u, err_flag);
-        // a worker warp whose 32 frames lie beyond frame 3000 reports the identities (lg2(0) = -inf, lg2(inf) = +inf)
-        mx = -__int_as_float(0x7f800000);
+      mbar_wait<WFE_TC_SLEEP_LONG>(&bar_st_full[nt & 1u], (nt >> 1) & 1u, err_flag);
+      const uint32_t id = s_red_id[nt & 1u];
+      if (id == kBooksDone) break;
+      // a worker warp whose 32 frames lie beyond frame 3000 reports the identities (lg2(0) = -inf, lg2(inf) = +inf)
+      float mx = -__int_as_float(0x7f800000);
 #pragma unroll
-        for (int w = 0; w < 8; ++w) mx = fmaxf(mx, s_red[nt & 1u][0][w]);
-        // the two epilogue warps of a frame quarter (w = quarter, quarter + 4) each finish part of every mel group
-        const int q = (lane >> 2) & 3, g = lane & 3;
-        mnb = __float_as_uint(fminf(s_red[nt & 1u][1 + g][q], s_red[nt & 1u][1 + g][q + 4]));
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_st_empty[nt & 1u]);
-        ++nt;
-      }
+      for (int w = 0; w < 8; ++w) mx = fmaxf(mx, s_red[nt & 1u][0][w]);
+      // the two epilogue warps of a frame quarter (w = quarter, quarter + 4) each finish part of every mel group;
+      // lanes 0..15: minimum of block (frame quarter lane / 4, mel group lane % 4)
+      const int q = (lane >> 2) & 3, g = lane & 3;
+      const uint32_t mnb = __float_as_uint(fminf(s_red[nt & 1u][1 + g][q], s_red[nt & 1u][1 + g][q + 4]));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_st_empty[nt & 1u]);
+      ++nt;
       if (lane == 0) p.tile_key[id] = f2key(mx);
       if (lane < kMinBlocks) p.tile_min[(size_t)id * kMinBlocks + lane] = mnb;
     }

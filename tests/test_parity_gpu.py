@@ -620,6 +620,33 @@ def test_clip_ending_in_the_pad_columns_of_its_tail_tile(fe128, monkeypatch):
         assert np.abs(first[b].cpu().numpy() - ologmel.logmel_clip(clip, 128, "fp64")).max() <= REGRESSION_TOL, b
 
 
+def test_normalised_ragged_batch_is_run_to_run_identical(fe128, monkeypatch):
+    # do_normalize sends every tile through the workers' staging path, where the normalisation pass revisits quads other
+    # threads wrote (a missing barrier there let raw samples land on top of normalised ones once in ~1000 batches):
+    # many repetitions, bit-identical, every clip against the CUDA-core kernel
+    rng = np.random.default_rng(11)
+    B = 60
+    lens = rng.integers(300, 480001, B).astype(np.int64)
+    dev = fe128.cuda_device()
+    starts = np.zeros(B, dtype=np.int64)
+    np.cumsum((lens[:-1] + 3) & ~3, out=starts[1:])
+    g = torch.Generator(device=dev)
+    g.manual_seed(11)
+    pcm = 0.1 * torch.randn(int(starts[-1] + lens[-1]), device=dev, generator=g) + 0.05
+    d_starts, d_lens = torch.from_numpy(starts).to(dev), torch.from_numpy(lens).to(dev)
+    ref, _ = _cuda_core_kernel(fe128, monkeypatch, pcm, d_starts, B, lengths=d_lens, do_normalize=True)
+    first = None
+    for _ in range(12):
+        feats, _ = fe128.logmel_device(pcm, d_starts, B, lengths=d_lens, do_normalize=True)
+        assert fe128.debug_kernel_error() == 0
+        assert first is None or torch.equal(feats, first)
+        first = feats
+    assert float((first - ref).abs().max()) <= TOL
+    clip = pcm[starts[7]:starts[7] + lens[7]].cpu().numpy()
+    clip = ologmel.zero_mean_unit_var(clip, len(clip))
+    assert np.abs(first[7].cpu().numpy() - ologmel.logmel_clip(clip, 128, "fp64")).max() <= TOL
+
+
 def test_speechlike_batch_1024_against_the_oracle_on_64_clips(fe128, monkeypatch):
     # BASELINE configs[2] size with the data-dependent path busy: 1024 ragged clips with speech-like dynamics (the clamp
     # pass rewrites most tiles), 64 of them against the oracle, all of them by the device-side invariants
