@@ -750,3 +750,18 @@ def test_two_byte_pcm_aligned_and_unaligned_agree_with_the_oracle(fe128, dtype):
         assert fe128.debug_kernel_error() == 0
         assert np.abs(feats.cpu().numpy() - ref).max() <= REGRESSION_TOL, align
         assert np.array_equal(mask.cpu().numpy(), mref), align
+
+
+def test_differential_fuzz_smoke():
+    # a few seconds of tools/fuzz_tc_vs_cc.py and tools/fuzz_host.py (fixed seeds): random ragged batches with garbage
+    # between the clips, tensor-core kernel against the CUDA-core kernel, and the host entry against the device entry.
+    # (The long runs are recorded in profiles/r02_fuzz_tc_vs_cc.txt; this keeps the tools alive and the suite honest.)
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for tool, args in (("fuzz_tc_vs_cc.py", ["4", "1234", "0.2"]), ("fuzz_host.py", ["3", "99"])):
+        res = subprocess.run([sys.executable, os.path.join(root, "tools", tool)] + args, capture_output=True, text=True,
+                             timeout=240)
+        tail = (res.stdout + res.stderr)[-1500:]
+        assert res.returncode == 0, tail
+        assert " 0 failures" in res.stdout and "FAIL" not in res.stdout, tail
