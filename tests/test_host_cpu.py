@@ -187,3 +187,15 @@ def test_two_rank_gloo_sharding_layout():
     assert n0 == n1 == 50 and (a0, b0, a1, b1) == (0, 50, 50, 100)
     labels = signals.label_ids(1337, 101, 5, 60)
     assert w0 == max(len(x) for x in labels[:50]) and w1 == max(len(x) for x in labels[50:100])
+
+
+def test_tools_compile():
+    # the timing / diagnostic / fuzz scripts under tools/ only run on a GPU box: at least keep them syntactically alive
+    import glob
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    scripts = sorted(glob.glob(os.path.join(root, "tools", "*.py"))) + [os.path.join(root, "bench.py"),
+                                                                         os.path.join(root, "__graft_entry__.py")]
+    assert len(scripts) > 10
+    for path in scripts:
+        with open(path) as f:
+            compile(f.read(), path, "exec")
