@@ -270,6 +270,10 @@ class WhisperFeatureExtractor:
             raise TypeError("`out` must be a contiguous float32 / float16 / bfloat16 tensor")
         mask = torch.empty((batch, h.n_frames), dtype=torch.int32, device=dev) if return_attention_mask else None
         scratch = torch.empty(max(h.scratch_bytes(batch), 4), dtype=torch.uint8, device=dev)
+        if os.environ.get("WFE_DEBUG_POISON_SCRATCH"):
+            # debugging aid: the allocator hands back the previous call's scratch, so a tile word the kernel forgot to
+            # write would still hold the RIGHT value of an identical earlier run
+            scratch.fill_(0xFF)
         stream = _cur_stream_ptr(dev)
         stats_ptr = None
         if do_normalize:
