@@ -83,7 +83,10 @@ def expected(tile: int, x: np.ndarray) -> np.ndarray:
 
 def run_case(tile: int, length: int, x_full: np.ndarray) -> None:
     mode = classify(tile, length)
-    if mode in ("silent", "sync"):
+    if mode == "silent":  # never loaded, never computed: its valid frames must see nothing but padding
+        assert not expected(tile, x_full[:length]).any(), (tile, length)
+        return
+    if mode == "sync":
         return
     s_begin = tile * TILE - NFFT // 2
     buf = np.concatenate([np.full(256, GARBAGE), x_full[:length], np.full(TILE + 1024, GARBAGE)])  # garbage all around
@@ -126,6 +129,19 @@ def test_last_tile_reflect_pad_for_every_length(signal):
     for length in list(range(s_begin - 450, s_begin + 450)) + list(range(s_begin + 450, NS - 450, 37)) + list(range(NS - 450, NS + 1)):
         run_case(23, length, signal)
         run_case(22, length, signal)
+
+
+def test_silent_tiles_see_only_padding(signal):
+    # around every tile's first sample, and around the reflect pad of the last tile, for every tile
+    for tile in range(1, 24):
+        s_begin = tile * TILE - NFFT // 2
+        for length in (1, s_begin - 1, s_begin, s_begin + 1):
+            for t in range(tile, 24):
+                if classify(t, length) == "silent":
+                    run_case(t, length, signal)
+    assert classify(23, 23 * TILE - NFFT // 2) == "silent" and classify(23, 23 * TILE - NFFT // 2 + 1) == "tail"
+    # a clip of one sample: only the first tile is not silent
+    assert [classify(t, 1) for t in range(24)] == ["sync"] + ["silent"] * 23
 
 
 def test_first_tile_head_patch(signal):
