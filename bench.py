@@ -510,6 +510,26 @@ def run_b200(args):
         return {"value": audio * steps / (total_ms * 1e-3), "ms_per_step": total_ms / steps, "kernel_ms": kern_ms,
                 "launches": int(launches), "steps": steps, "kernel_timeouts": timeouts}
 
+    def cross_check(d_pcm, out, offs=None, lengths=None, batch=B):
+        """Outside every timed region: the timed output against the CUDA-core kernel (WFE_DISABLE_TC=1: the product's
+        second, independent implementation of the same arithmetic) on the same input, max |difference| over the whole
+        batch.  Reporting only: never fails the bench; the environment switch is restored whatever happens."""
+        prev = os.environ.get("WFE_DISABLE_TC")
+        try:
+            os.environ["WFE_DISABLE_TC"] = "1"
+            ref, _ = fe.logmel_device(d_pcm, d_offs if offs is None else offs, batch, lengths=lengths)
+            torch.cuda.synchronize()
+            diff = float((out - ref).abs().max())
+            del ref
+            return diff
+        except Exception as exc:  # noqa: BLE001
+            return f"unavailable: {type(exc).__name__}: {exc}"[:200]
+        finally:
+            if prev is None:
+                os.environ.pop("WFE_DISABLE_TC", None)
+            else:
+                os.environ["WFE_DISABLE_TC"] = prev
+
     def roofline_of(w, batch=B, alg_bytes=None):
         alg = batch * bytes_per_clip if alg_bytes is None else alg_bytes
         ach = alg / (w["kernel_ms"] * 1e-3) / 1e9
@@ -524,11 +544,13 @@ def run_b200(args):
         workloads["noise"] = device_workload(d_noise, args.steps)
         span = float((d_out.amax(dim=(1, 2)) - d_out.amin(dim=(1, 2))).max())
         assert torch.isfinite(d_out).all() and 0.0 < span <= 2.0 + 1e-5, span  # the timed output is real
+        workloads["noise"]["max_abs_diff_vs_cuda_core_kernel"] = cross_check(d_noise, d_out)
         ref_out = d_out.clone() if args.workload != "noise" else None
     if args.workload in ("all", "headline", "speechlike"):
         workloads["speechlike"] = device_workload(d_speech, args.steps)
         span = float((d_out.amax(dim=(1, 2)) - d_out.amin(dim=(1, 2))).max())
         assert torch.isfinite(d_out).all() and 0.0 < span <= 2.0 + 1e-5, span
+        workloads["speechlike"]["max_abs_diff_vs_cuda_core_kernel"] = cross_check(d_speech, d_out)
     if args.workload in ("all", "config3"):
         # BASELINE configs[2]: 1024 clips of 1-30 s, padded to 3000 frames, attention masks + labels
         Bc = 1024
@@ -544,6 +566,8 @@ def run_b200(args):
         wc["clips_per_s"] = Bc * world / (wc["ms_per_step"] * 1e-3)
         wc["roofline"] = roofline_of(wc, alg_bytes=int(lens_c.sum()) * 4 + Bc * n_mel * N_FRAMES * 4)
         wc["note"] = "1024 ragged clips (1-30 s); every clip still writes 3000 frames; `value` counts real audio seconds"
+        wc["max_abs_diff_vs_cuda_core_kernel"] = cross_check(d_pcm_c, d_out_c, offs=torch.from_numpy(starts).to(dev),
+                                                             lengths=torch.from_numpy(lens_c).to(dev), batch=Bc)
         workloads["config3_ragged_1024"] = wc
         del d_pcm_c, d_out_c
     if args.workload == "shard":
@@ -731,7 +755,7 @@ def run_b200(args):
                                "kernel_ms_per_launch": w_["kernel_ms"], "roofline_frac": w_["roofline"]["frac"],
                                "achieved_gbs": w_["roofline"]["achieved_gbs"],
                                **{x: w_[x] for x in ("clips_per_s", "note", "clips", "clips_per_rank", "kernel_timeouts",
-                                                     "remeasured_after_kernel_timeout",
+                                                     "remeasured_after_kernel_timeout", "max_abs_diff_vs_cuda_core_kernel",
                                                      "wall_s_including_generation_and_checks") if x in w_}}
                           for k_, w_ in workloads.items()},
             "clocks": clocks,
