@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libwfe.so")
-SOURCES = ["wfe_api.cu", "wfe_codelets.cuh", "wfe_logmel.cuh", "wfe_logmel_tc.cuh", "wfe_tc_epilogue_gen.inc", "wfe_collate.cuh",
+SOURCES = ["wfe_api.cu", "wfe_codelets.cuh", "wfe_logmel.cuh", "wfe_logmel_tc.cuh", "wfe_tc_epilogue_gen.inc", "wfe_collate.cuh", "wfe_copy_pool.h",
            os.path.join("..", "..", "include", "wfe.h")]
 
 

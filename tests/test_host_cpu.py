@@ -199,3 +199,31 @@ def test_tools_compile():
     for path in scripts:
         with open(path) as f:
             compile(f.read(), path, "exec")
+
+
+def test_staging_copy_pool_stress_and_thread_sanitizer(tmp_path):
+    # the host entry's staging threads (asr-finetune_b200/csrc/wfe_copy_pool.h, plain C++): random batches back to back,
+    # every destination byte checked; then the same under ThreadSanitizer (an earlier lock-free piece claim could pair an
+    # index of the previous batch with the new piece table when a worker woke up late)
+    import ctypes
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "tests", "host", "copy_pool_host.cpp")
+    gxx = shutil.which("g++")
+    assert gxx, "g++ is part of the image"
+    lib_path = str(tmp_path / "libcopy_pool_host.so")
+    subprocess.run([gxx, "-O2", "-std=c++17", "-pthread", "-shared", "-fPIC", "-o", lib_path, src], check=True)
+    lib = ctypes.CDLL(lib_path)
+    lib.copy_pool_stress.restype = ctypes.c_int
+    lib.copy_pool_stress.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_int]
+    for threads in (0, 1, 3, 8):
+        assert lib.copy_pool_stress(threads, 120, 1000 + threads, 0) == 0
+        assert lib.copy_pool_stress(threads, 120, 2000 + threads, 1) == 0
+    exe = str(tmp_path / "copy_pool_tsan")
+    res = subprocess.run([gxx, "-O1", "-g", "-std=c++17", "-pthread", "-fsanitize=thread", "-DCOPY_POOL_MAIN", "-o", exe, src],
+                         capture_output=True, text=True)
+    if res.returncode != 0:
+        pytest.skip("ThreadSanitizer runtime not available: " + res.stderr[-200:])
+    run = subprocess.run([exe, "6", "25"], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0 and "0 bad batches" in run.stdout and "ThreadSanitizer" not in run.stderr, run.stderr[-2000:]
